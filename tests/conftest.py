@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "torch-gaussian-splatting-rasterizer_b200")
+for p in (os.path.join(ROOT, "tests", "golden"), ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+
+    def load(name):
+        return dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"), allow_pickle=False))
+
+    return load

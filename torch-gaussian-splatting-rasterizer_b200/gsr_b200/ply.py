@@ -1,0 +1,130 @@
+"""Minimal binary-little-endian PLY reader/writer for 3DGS point clouds.
+
+The reference reads its Gaussians through the third-party ``plyfile`` package
+(/root/reference/rasterize.py:353, /root/reference/utils.py:21-27), which is not
+vendored and not installed here.  Only one thing about that package matters to
+the render path: ``PlyData.read(path).elements[0][name]`` yields one numpy
+column per vertex property.  This module provides exactly that for the
+3DGS layout (62 little-endian float32 properties per vertex):
+
+    x y z  nx ny nz  f_dc_0..2  f_rest_0..44  opacity  scale_0..2  rot_0..3
+
+``PlyData`` / ``PlyElement`` mirror the two names the reference imports.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+_NP_OF_PLY = {
+    "float": "<f4", "float32": "<f4", "double": "<f8", "float64": "<f8",
+    "uchar": "u1", "uint8": "u1", "char": "i1", "int8": "i1",
+    "short": "<i2", "int16": "<i2", "ushort": "<u2", "uint16": "<u2",
+    "int": "<i4", "int32": "<i4", "uint": "<u4", "uint32": "<u4",
+}
+
+GS_PROPERTIES: List[str] = (
+    ["x", "y", "z", "nx", "ny", "nz"]
+    + [f"f_dc_{i}" for i in range(3)]
+    + [f"f_rest_{i}" for i in range(45)]
+    + ["opacity"]
+    + [f"scale_{i}" for i in range(3)]
+    + [f"rot_{i}" for i in range(4)]
+)
+assert len(GS_PROPERTIES) == 62
+
+
+class PlyElement:
+    """One PLY element: column access by property name (``el["x"]`` -> ndarray)."""
+
+    def __init__(self, name: str, data: np.ndarray):
+        self.name = name
+        self.data = data  # numpy structured array, one field per property
+
+    def __getitem__(self, key: str) -> np.ndarray:
+        return self.data[key]
+
+    def __len__(self) -> int:
+        return int(self.data.shape[0])
+
+    @property
+    def properties(self) -> Sequence[str]:
+        return self.data.dtype.names
+
+
+class PlyData:
+    """``PlyData.read(path).elements[0]["opacity"]`` as the reference expects."""
+
+    def __init__(self, elements: List[PlyElement]):
+        self.elements = elements
+
+    def __getitem__(self, name: str) -> PlyElement:
+        for el in self.elements:
+            if el.name == name:
+                return el
+        raise KeyError(name)
+
+    @staticmethod
+    def read(path: str) -> "PlyData":
+        return PlyData(_read_elements(path))
+
+
+def _read_elements(path: str) -> List[PlyElement]:
+    with open(path, "rb") as fh:
+        magic = fh.readline().strip()
+        if magic != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        layout: List[Dict] = []
+        while True:
+            line = fh.readline()
+            if not line:
+                raise ValueError(f"{path}: unterminated PLY header")
+            tok = line.decode("ascii").split()
+            if not tok or tok[0] == "comment" or tok[0] == "obj_info":
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                layout.append({"name": tok[1], "count": int(tok[2]), "props": []})
+            elif tok[0] == "property":
+                if tok[1] == "list":
+                    raise ValueError(f"{path}: list properties are not supported")
+                layout[-1]["props"].append((tok[2], _NP_OF_PLY[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if fmt != "binary_little_endian":
+            raise ValueError(f"{path}: only binary_little_endian PLY is supported (got {fmt})")
+        out = []
+        for el in layout:
+            dt = np.dtype(el["props"])
+            buf = fh.read(dt.itemsize * el["count"])
+            if len(buf) != dt.itemsize * el["count"]:
+                raise ValueError(f"{path}: truncated element {el['name']}")
+            out.append(PlyElement(el["name"], np.frombuffer(buf, dtype=dt, count=el["count"])))
+        return out
+
+
+def write_gaussian_ply(path: str, table: np.ndarray) -> None:
+    """Write an ``[N, 62]`` float32 table in the 3DGS vertex layout."""
+    table = np.ascontiguousarray(table, dtype="<f4")
+    if table.ndim != 2 or table.shape[1] != len(GS_PROPERTIES):
+        raise ValueError("expected an [N, 62] table")
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    head = ["ply", "format binary_little_endian 1.0", f"element vertex {table.shape[0]}"]
+    head += [f"property float {p}" for p in GS_PROPERTIES]
+    head += ["end_header", ""]
+    with open(path, "wb") as fh:
+        fh.write("\n".join(head).encode("ascii"))
+        fh.write(table.tobytes())
+
+
+def read_gaussian_table(path: str) -> np.ndarray:
+    """Read the vertex element as a dense ``[N, P]`` float32 table plus check the 3DGS columns exist."""
+    el = PlyData.read(path).elements[0]
+    missing = [p for p in GS_PROPERTIES if p not in el.properties and p not in ("nx", "ny", "nz")]
+    if missing:
+        raise ValueError(f"{path}: missing 3DGS properties {missing[:4]}...")
+    return el
