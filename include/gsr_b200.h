@@ -1,0 +1,184 @@
+/*
+ * gsr_b200.h - C ABI of libgsr_b200.so, the B200 (sm_100a) render path that replaces the
+ * reference's per-Gaussian PyTorch loop.
+ *
+ * The reference (arnaudstiegler/torch-gaussian-splatting-rasterizer) has no FFI: its interface for
+ * this path is a set of module-level Python functions.  Each entry point below names the reference
+ * lines it replaces (citations into /root/reference/); INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns a gsr_status (0 = ok); no C++ exceptions cross the boundary;
+ *    gsr_last_error() returns a thread-local message for the last non-zero status.
+ *  - all data pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *    buffer (inputs, outputs, workspace).  Nothing is allocated and nothing synchronises inside the
+ *    device entry points: work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - float tensors are f32; strides are in ELEMENTS, so any torch view can be passed without a copy.
+ *  - Gaussian parameters are the raw 3DGS PLY values: log-scales, un-normalised quaternions (w,x,y,z),
+ *    opacity logits, SH coefficients indexed [n, k(16), c(3)].
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+#define GSR_TILE 16 /* BLOCK_SIZE, rasterize.py:34 */
+
+typedef enum gsr_status {
+  GSR_OK = 0,
+  GSR_ERR_INVALID_ARGUMENT = 1,
+  GSR_ERR_CUDA = 2,
+  GSR_ERR_WORKSPACE_TOO_SMALL = 3,
+  GSR_ERR_DUP_OVERFLOW = 4 /* reported through gsr_frame_info.status, see gsr_render_fwd */
+} gsr_status;
+
+/* Per-view constants, computed on the host exactly as the reference does (rasterize.py:336-364). */
+typedef struct gsr_camera {
+  float w2c_t[16];     /* get_world_to_camera_matrix(q,t).T, row-major (row-vector convention)  :361 */
+  float full_t[16];    /* w2c_t @ get_projection_matrix(fovx,fovy).T                            :364 */
+  float cam_center[3]; /* inverse(w2c_t)[3,:3]                                 spherical_harmonics.py:35 */
+  float focal_x, focal_y; /* f32(fx/2), f32(fy/2)                                               :216 */
+  float limx, limy;    /* f32(1.3*tan(fov/2))                                                   :210-211 */
+  int32_t width, height; /* rendered image size                                                 :338 */
+  int32_t sh_degree;   /* 0..3 (the reference hard-codes 3,                                     :368) */
+  int32_t reserved;
+} gsr_camera;
+
+/* Strided views of the Gaussian parameters (element strides). */
+typedef struct gsr_gaussians {
+  int64_t n;
+  const float *xyz;           int64_t xyz_sn, xyz_sc;       /* [n,3]                    :354-356 */
+  const float *log_scales;    int64_t scale_sn, scale_sc;   /* [n,3]  scale_0..2        :97-99   */
+  const float *rots;          int64_t rot_sn, rot_sc;       /* [n,4]  rot_0..3 (w,x,y,z) :100-109 */
+  const float *opacity_logit; int64_t opacity_sn;           /* [n]    opacity           :358     */
+  const float *sh;            int64_t sh_sn, sh_sk, sh_sc;  /* [n,16,3] utils.py:21-31 (planar [3,16,n] view is the fast layout) */
+} gsr_gaussians;
+
+/* Written by the device at the end of a frame (device memory; copy back when convenient). */
+typedef struct gsr_frame_info {
+  uint32_t status;        /* gsr_status: GSR_ERR_DUP_OVERFLOW when n_dup exceeded max_dup (image is then invalid) */
+  uint32_t n_visible;     /* Gaussians that touch at least one tile */
+  uint32_t n_dup;         /* (Gaussian, tile) pairs produced by binning */
+  uint32_t reserved;
+  uint64_t warp_evals;    /* Gaussian-pixel evaluations executed by blend, counted at warp granularity (x32) */
+  uint64_t pixel_evals;   /* evaluations executed by pixels that had not yet terminated */
+} gsr_frame_info;
+
+/* Per-Gaussian record consumed by the blend kernel: 3 x float4, 16-byte aligned. */
+#define GSR_REC_FLOATS 12
+/*  [0] mean2d.x  [1] mean2d.y  [2] conic a  [3] conic c      (sigmas = (a, c, b), rasterize.py:404-411)
+ *  [4] conic b   [5] opacity   [6] r        [7] g
+ *  [8] b(lue)    [9] depth z   [10] radius  [11] 0                                                   */
+
+const char *gsr_last_error(void);
+int gsr_abi_version(void);
+/* SM count etc. of the current device; returns GSR_ERR_CUDA when no device is usable. */
+int gsr_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+/* Measured FP32 FMA throughput of the current device (TFLOP/s, FMA = 2) and the SM clock it implies: the
+ * denominator of the blend stage's roofline.  Synchronises; diagnostics only. */
+int gsr_fp32_fma_peak(double *tflops, double *sm_mhz_effective);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole frame: rasterize.py:354-452 for one view.  image[H,W,3] is the reference's
+ * screen.transpose(1,0) (:471); final_T[H,W] (may be NULL) is its opacity_buffer transposed;
+ * n_contrib[H,W] (may be NULL) is the position in the pixel's tile list after which blending stopped.
+ * first_rank/last_rank restrict blending to Gaussians whose global depth rank r satisfies
+ * first_rank <= r < last_rank (progressive renders, :448-452); pass 0 and UINT32_MAX for everything.
+ * tile_row_begin/end restrict the frame to a band of tile rows (multi-GPU band sharding); rows outside
+ * the band are left untouched in image.  info_dev (device, may be NULL) receives counters.
+ * --------------------------------------------------------------------------------------------- */
+int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
+int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                   size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                   uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                   gsr_frame_info *info_dev, void *stream);
+
+/* Same frame with HOST buffers: uploads the parameters, renders, downloads the image, synchronises.
+ * This is the call that stands where the reference's run_rasterization body stands (:354-452). */
+int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t max_dup, float *image_host,
+                    gsr_frame_info *info_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stages (each usable on its own; the tests drive them one by one)
+ * --------------------------------------------------------------------------------------------- */
+
+/* Fused per-Gaussian preprocess: :97-120 (Sigma), :358 (sigmoid), :371-420 (projection, cull, EWA, radius,
+ * tile rect, conic, skip rule :441) and spherical_harmonics.py:27-73.
+ *  depth_key[n]      u32, order-preserving bits of z_cam (:424)
+ *  tiles_touched[n]  u32, 0 for culled / skipped / off-screen Gaussians
+ *  rect[n,4]         u16 tile rect (x0,y0,x1,y1), clipped to the tile grid and to [row_begin,row_end)
+ *  rec[n,12]         blend record (written for visible Gaussians only)
+ * optional debug outputs (may be NULL): cov3d[n,9], cov2d[n,4] (after cull zeroing), tile_rect_raw[n,4] i32
+ * (the reference's compute_covering_bbox result), radius[n]. */
+int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t tile_row_begin, int32_t tile_row_end,
+                       uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, float *rec, float *cov3d,
+                       float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, void *stream);
+
+/* spherical_harmonics.sh_to_rgb (spherical_harmonics.py:27-73): rgb[n,3] contiguous. */
+int gsr_sh_fwd(int64_t n, const float *xyz, int64_t xyz_sn, int64_t xyz_sc, const float *sh, int64_t sh_sn,
+               int64_t sh_sk, int64_t sh_sc, const float *cam_center_host3, int32_t degree, float *rgb, void *stream);
+
+/* Stable LSB radix sort of (u32 key, u32 value) pairs on bits [begin_bit, end_bit).  values_in may be NULL
+ * (then values are 0..n-1).  Result lands in keys_out/values_out.  n_dev (device u32, may be NULL) overrides n
+ * with a device-side count <= n.  Scratch comes from workspace (gsr_sort_workspace_bytes). */
+int gsr_sort_workspace_bytes(int64_t n, size_t *bytes);
+int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
+                   uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int32_t begin_bit,
+                   int32_t end_bit, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Binning: global stable depth sort (:424-425, ties by Gaussian index), duplication into (tile, Gaussian) pairs
+ * in depth order, stable sort by tile, tile range extraction.  Equivalent to sorting 64-bit (tile|depth) keys.
+ *  depth_order[n]     u32 Gaussian ids in ascending depth                 (out)
+ *  blend_rank[n]      u32 rank of each visible Gaussian among the Gaussians the reference's loop would
+ *                     blend, in blend order (out, may be NULL; feeds progressive renders)
+ *  tile_gids[max_dup] u32 Gaussian ids grouped by tile, depth-sorted      (out)
+ *  tile_ranges[tiles,2] u32 [begin,end) into tile_gids                    (out)
+ *  info_dev->n_dup / n_visible / status are filled (info_dev may be NULL). */
+int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
+int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *tiles_touched, const uint16_t *rect,
+            int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order, uint32_t *blend_rank,
+            uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
+            size_t workspace_bytes, void *stream);
+
+/* Per-16x16-tile front-to-back alpha blend (:255-305, :436-446).  Pixels x >= W-1 or y >= H-1 are written
+ * as zero (the reference never writes them).  When blend_rank is given, only Gaussians with
+ * first_rank <= blend_rank < last_rank are blended (the state of the reference's screen after last_rank
+ * loop iterations that were not skipped, :448-452). */
+int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const uint32_t *tile_ranges, int32_t width,
+                  int32_t height, int32_t tile_row_begin, int32_t tile_row_end, const uint32_t *blend_rank,
+                  uint32_t first_rank, uint32_t last_rank, float *image, float *final_T, uint32_t *n_contrib,
+                  gsr_frame_info *info_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Drop-in helpers behind the reference's module-level functions
+ * --------------------------------------------------------------------------------------------- */
+/* get_covariance_matrix_from_mesh (:89-120): cov3d[n,3,3]. */
+int gsr_cov3d_fwd(int64_t n, const float *log_scales, int64_t s_sn, int64_t s_sc, const float *rots, int64_t r_sn,
+                  int64_t r_sc, float *cov3d, void *stream);
+/* quaternion_to_rotation_matrix (:41-56): q[4,n] strided -> R[3,3,n] contiguous, no normalisation. */
+int gsr_quat_to_rotmat(int64_t n, const float *q, int64_t q_sc, int64_t q_sn, float *rot, void *stream);
+/* project_to_camera_space (:80-86) and the clip-space product (:374): out[n,cols] = p @ M[:3,:cols] + M[3,:cols],
+ * M a HOST row-major 4x4. */
+int gsr_affine_fwd(int64_t n, const float *xyz, int64_t sn, int64_t sc, const float *m_host16, int32_t cols,
+                   float *out, void *stream);
+/* compute_2d_covariance (:201-252): cov3d[n,3,3] + camera-space means[n,3] -> cov2d[n,2,2]. */
+int gsr_cov2d_fwd(int64_t n, const float *cov3d, const float *cam_means, const gsr_camera *cam, float *cov2d,
+                  void *stream);
+/* compute_covering_bbox (:154-198): -> tile rect [n,4] int64. */
+int gsr_bbox_fwd(int64_t n, const float *mean2d, const float *cov2d, int32_t width, int32_t height, int64_t *rect,
+                 void *stream);
+/* rasterize_gaussian (:255-305): blend ONE Gaussian into the x-major screen[W,H,3] / opacity_buffer[W,H]. */
+int gsr_blend_one(const int64_t *bbox4_host, const float *mean2d_host2, const float *conic_host3,
+                  const float *rgb_host3, float opacity, int32_t width, int32_t height, float *screen,
+                  float *opacity_buffer, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */

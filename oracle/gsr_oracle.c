@@ -18,8 +18,8 @@
  * reference's torch-CPU execution performs it: sgemm-backed products are
  * fmaf chains in ascending k with a separately rounded "+ row"; 3x3 bmm products are plain
  * multiply/add in ascending k; scalar/tensor divisions are reciprocal-then-multiply.
- * Build with -ffp-contract=off (see oracle/build.py).  exp/sigmoid use libm expf: torch routes
- * them through MKL VML, which is closed source, so exp-derived values agree to <= 1 ulp, not bitwise.
+ * Build with -ffp-contract=off (see oracle/build.py).  exp-derived values agree with the reference to
+ * <= 1 ulp, not always bitwise (see exp_scale / exp_sleef_u10 below); everything else is bit-exact.
  *
  * PINNING: tests/test_oracle_cpu.py checks this file against golden vectors captured from the
  * unmodified reference (tests/golden/make_golden.py) - depth bit-exact, images to 1e-5.
@@ -56,6 +56,40 @@ static const float SH2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.315391
                              -1.0925484305920792f, 0.5462742152960396f};
 static const float SH3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                              -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+/*
+ * exp as the reference's torch-CPU build evaluates it:
+ *  - torch.exp on a contiguous f32 tensor (rasterize.py:97) goes to MKL VML (high-accuracy mode, closed
+ *    source).  It differs from the correctly rounded result in ~1.1 % of inputs (measured), so the best
+ *    restatement is the correctly rounded value: double exp, rounded once to f32.
+ *  - torch.sigmoid (rasterize.py:358) is 1/(1+e) with e from the vectorised Sleef expf (u10, FMA form).
+ *    The sequence below reproduces it bit-for-bit on the vector body (2M-sample check: only the <16-element
+ *    scalar tails of each thread chunk differ, by 1 ulp, because torch runs those through libm).
+ */
+static inline float exp_scale(float x) { return (float)exp((double)x); }
+
+static inline float exp_sleef_u10(float d) {
+  float qf = rintf(d * 1.442695040888963407359924681001892137426645954152985934135449406931f);
+  int q = (int)qf;
+  float s = fmaf(qf, -0.693145751953125f, d);
+  s = fmaf(qf, -1.428606765330187045e-06f, s);
+  float u = 0.000198527617612853646278381f;
+  u = fmaf(u, s, 0.00139304355252534151077271f);
+  u = fmaf(u, s, 0.00833336077630519866943359f);
+  u = fmaf(u, s, 0.0416664853692054748535156f);
+  u = fmaf(u, s, 0.166666671633720397949219f);
+  u = fmaf(u, s, 0.5f);
+  u = 1.0f + fmaf(s * s, u, s);
+  union { float f; int32_t i; } a, b;
+  a.i = ((q >> 1) + 0x7f) << 23;
+  b.i = ((q - (q >> 1)) + 0x7f) << 23;
+  u = (u * a.f) * b.f;
+  if (d < -104.0f) u = 0.0f;
+  if (d > 100.0f) u = INFINITY;
+  return u;
+}
+
+static inline float sigmoid_ref(float x) { return 1.0f / (1.0f + exp_sleef_u10(-x)); }
 
 static inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -115,7 +149,7 @@ void gsr_oracle_sh(int64_t n, const float *xyz, const float *sh, int64_t sn, int
 
 /* rasterize.py:41-56,97-120 : Sigma (row-major 3x3) from log-scales and an un-normalised quaternion. */
 static void covariance3d(const float *ls, const float *rot, float *S) {
-  float s[3] = {expf(ls[0]), expf(ls[1]), expf(ls[2])};
+  float s[3] = {exp_scale(ls[0]), exp_scale(ls[1]), exp_scale(ls[2])};
   float nrm = sqrtf(((rot[0] * rot[0] + rot[1] * rot[1]) + rot[2] * rot[2]) + rot[3] * rot[3]);
   float den = nrm > 1e-12f ? nrm : 1e-12f;
   float w = rot[0] / den, x = rot[1] / den, y = rot[2] / den, z = rot[3] / den;
@@ -231,7 +265,7 @@ void gsr_oracle_preprocess(int64_t n, const float *xyz, const float *log_scales,
     if (tile_rect) for (int j = 0; j < 4; ++j) tile_rect[4 * i + j] = (int32_t)rect[j];
     if (pixel_bbox) for (int j = 0; j < 4; ++j) pixel_bbox[4 * i + j] = (int32_t)bb[j];
     if (rgb) sh_colour(p, sh + i * sn, sk, sc, k->cam_center, k->sh_degree, rgb + 3 * i);
-    if (opacity) opacity[i] = 1.0f / (1.0f + expf(-opacity_logit[i]));
+    if (opacity) opacity[i] = sigmoid_ref(opacity_logit[i]);
     if (depth) depth[i] = cam[2];
     if (radius) radius[i] = r;
     if (skip) skip[i] = (uint8_t)(area == 0 || ca == 0.0f || cc == 0.0f || cb == 0.0f);

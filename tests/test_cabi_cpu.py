@@ -1,0 +1,132 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports every symbol the header declares;
+argument validation that needs no GPU; host-side camera math against the reference's captured values."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, build_case
+from gsr_b200 import _cabi, build, camera
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gsr_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _cabi.load()
+
+
+def _declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in gsr_b200.h but not exported"
+    bound = set(_cabi.PROTOTYPES) | {"gsr_last_error"}
+    assert set(names) == bound, set(names) ^ bound
+
+
+def test_abi_version_and_struct_sizes(lib):
+    assert lib.gsr_abi_version() == 1
+    assert ctypes.sizeof(camera.CameraStruct) == 4 * (16 + 16 + 3 + 2 + 2) + 16
+    assert ctypes.sizeof(_cabi.Gaussians) == 8 * 16
+    assert ctypes.sizeof(_cabi.FrameInfo) == 32
+
+
+def test_invalid_arguments_are_reported_not_crashed(lib):
+    need = ctypes.c_size_t()
+    assert lib.gsr_render_workspace_bytes(-1, 64, 64, 100, ctypes.byref(need)) == _cabi.GSR_ERR_INVALID_ARGUMENT
+    assert b"invalid argument" in lib.gsr_last_error()
+    assert lib.gsr_render_workspace_bytes(1000, 64, 64, 8000, ctypes.byref(need)) == _cabi.GSR_OK
+    assert need.value > 1000 * 48
+    with pytest.raises(_cabi.GsrError):
+        _cabi.call("gsr_sort_pairs", None, None, None, None, None, None, 10, None, 0, 32, None, 0, None)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import rasterize
+    import spherical_harmonics
+
+    with pytest.raises(_cabi.GsrError):
+        spherical_harmonics.sh_to_rgb(torch.zeros(4, 3), torch.zeros(4, 16, 3), torch.eye(4), degree=3)
+    with pytest.raises(_cabi.GsrError):
+        rasterize.render(torch.zeros(4, 3), torch.zeros(4, 3), torch.ones(4, 4), torch.zeros(4), torch.zeros(4, 16, 3),
+                         [1, 0, 0, 0], [0, 0, 4], 100.0, 100.0, 64, 64, 32, 32)
+
+
+@pytest.mark.parametrize("name", ["synth_small", "orbit_b", "tilted"])
+def test_host_camera_reproduces_reference_projection(name, golden):
+    """cam_means / mean2d captured from the reference are exact functions of the camera struct: recompute them in
+    numpy with the documented fma recipe and require bit equality."""
+    c = CASES[name]
+    cloud, intr, view = build_case(c)
+    g = golden(name)
+    cam = camera.camera_for(intr, view, 3)
+    m = np.array(list(cam.w2c_t), dtype=np.float32).reshape(4, 4)
+    x, y, z = (cloud.xyz[:, i].astype(np.float64) for i in range(3))
+    # fma in float64 of f32 inputs is exact up to the final rounding: products of two f32 fit in f64
+    def f32(a):
+        return a.astype(np.float32)
+    acc = f32(x * m[0, 2].astype(np.float64))
+    acc = f32(y * np.float64(m[1, 2]) + acc.astype(np.float64))
+    acc = f32(z * np.float64(m[2, 2]) + acc.astype(np.float64))
+    depth = acc + m[3, 2]
+    assert np.array_equal(depth.view(np.int32), g["depth"].view(np.int32))
+
+
+def test_drop_in_modules_expose_reference_names():
+    import data_reader
+    import rasterize
+    import spherical_harmonics
+    import utils
+
+    for name in ("quaternion_to_rotation_matrix", "get_world_to_camera_matrix", "project_to_camera_space",
+                 "get_covariance_matrix_from_mesh", "get_projection_matrix", "compute_covering_bbox",
+                 "compute_2d_covariance", "rasterize_gaussian", "run_rasterization", "render", "Z_FAR", "Z_NEAR",
+                 "GAUSSIAN_SPREAD", "BLOCK_SIZE", "MAX_GAUSSIAN_DENSITY", "MIN_ALPHA"):
+        assert hasattr(rasterize, name), name
+    assert (rasterize.Z_FAR, rasterize.Z_NEAR, rasterize.GAUSSIAN_SPREAD, rasterize.BLOCK_SIZE) == (100.0, 0.01, 3, 16)
+    assert rasterize.MAX_GAUSSIAN_DENSITY == 0.99 and rasterize.MIN_ALPHA == 1 / 255
+    for name in ("sh_to_rgb", "SH_0", "SH_C1", "SH_C2", "SH_C3"):
+        assert hasattr(spherical_harmonics, name)
+    assert len(spherical_harmonics.SH_C2) == 5 and len(spherical_harmonics.SH_C3) == 7
+    for name in ("read_color_components", "read_scene"):
+        assert hasattr(utils, name)
+    for name in ("Camera", "BaseImage", "read_extrinsics_binary", "read_intrinsics_binary", "CAMERA_MODEL_IDS"):
+        assert hasattr(data_reader, name)
+    opts = {p.name for p in rasterize.run_rasterization.params}
+    assert opts == {"input_dir", "trained_model_path", "output_path", "scene_index", "scale_factor", "generate_video"}
+
+
+def test_scene_io_round_trip(tmp_path):
+    import utils
+    from gsr_b200 import scenes
+    from gsr_b200.ply import PlyData
+
+    cloud = scenes.synth_v1(257, 5)
+    intr = scenes.Intrinsics.synthetic(70, 50)
+    views = scenes.orbit_views(3, total=8)
+    root = scenes.write_scene_dir(str(tmp_path), cloud, intr, views)
+    imgs, cams = utils.read_scene(root)
+    assert sorted(imgs) == [0, 1, 2] and list(cams) == [1]
+    assert cams[1].model == "PINHOLE" and (cams[1].width, cams[1].height) == (140, 100)
+    assert np.allclose(cams[1].params, [168.0, 168.0, 70.0, 50.0])
+    for v in views:
+        assert np.array_equal(imgs[v.image_id].qvec, v.qvec) and np.array_equal(imgs[v.image_id].tvec, v.tvec)
+        assert imgs[v.image_id].name == "view.png" and imgs[v.image_id].camera_id == 1
+    ply = PlyData.read(os.path.join(root, "point_cloud/iteration_30000/point_cloud.ply"))
+    assert np.array_equal(ply.elements[0]["opacity"], cloud.opacity)
+    sh = utils.read_color_components(ply)
+    assert tuple(sh.shape) == (257, 16, 3) and sh.stride() == (1, 257, 16 * 257)
+    assert np.array_equal(sh.numpy(), cloud.sh_planar().transpose(2, 1, 0))

@@ -1,0 +1,234 @@
+// api.cu - C-ABI glue: error strings, device info, whole-frame driver and the host-buffer entry point.
+#include <stdarg.h>
+#include <string.h>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  va_end(ap);
+}
+
+struct FrameLayout {
+  size_t depth_key, tiles_touched, rect, rec, order, blend_rank, tile_gids, tile_ranges, bin, total;
+  size_t bin_bytes;
+};
+
+static int frame_layout(int64_t n, int width, int height, int64_t max_dup, FrameLayout *L) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  const size_t n1 = (size_t)(n > 0 ? n : 1), d1 = (size_t)(max_dup > 0 ? max_dup : 1);
+  const TileGrid tg = make_grid(width, height);
+  L->depth_key = take(4 * n1);
+  L->tiles_touched = take(4 * n1);
+  L->rect = take(8 * n1);
+  L->rec = take(sizeof(float) * GSR_REC_FLOATS * n1);
+  L->order = take(4 * n1);
+  L->blend_rank = take(4 * n1);
+  L->tile_gids = take(4 * d1);
+  L->tile_ranges = take(8 * (size_t)tg.tiles_x * tg.tiles_y);
+  int rc = gsr_bin_workspace_bytes(n, width, height, max_dup, &L->bin_bytes);
+  if (rc) return rc;
+  L->bin = take(L->bin_bytes);
+  L->total = off;
+  return GSR_OK;
+}
+
+// FP32 FMA throughput probe: the denominator of the blend kernel's roofline (MEASURED_PEAKS.json has no FP32 figure).
+__global__ void __launch_bounds__(256) fma_probe_kernel(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f,
+        x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" int gsr_fp32_fma_peak(double *tflops, double *sm_mhz_effective) {
+  GSR_REQUIRE(tflops, "null pointer");
+  int dev = 0, sms = 0, khz = 0;
+  GSR_CHECK_CUDA(cudaGetDevice(&dev));
+  GSR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GSR_CHECK_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  (void)khz;
+  float *d = nullptr;
+  GSR_CHECK_CUDA(cudaMalloc(&d, 16));
+  cudaEvent_t e0, e1;
+  GSR_CHECK_CUDA(cudaEventCreate(&e0));
+  GSR_CHECK_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    GSR_CHECK_CUDA(cudaEventRecord(e0));
+    fma_probe_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+    GSR_CHECK_CUDA(cudaEventRecord(e1));
+    GSR_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GSR_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 64.0 * iters * 256.0 * blocks;
+    const double t = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && t > best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  if (sm_mhz_effective) *sm_mhz_effective = best * 1e12 / (2.0 * 128.0 * sms) / 1e6;
+  return GSR_OK;
+}
+
+extern "C" const char *gsr_last_error(void) { return g_error; }
+extern "C" int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+
+extern "C" int gsr_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes) {
+  int dev = 0;
+  GSR_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  GSR_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+  return GSR_OK;
+}
+
+extern "C" int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes) {
+  GSR_REQUIRE(bytes && n >= 0 && width > 0 && height > 0 && max_dup > 0, "bad arguments");
+  FrameLayout L;
+  int rc = frame_layout(n, width, height, max_dup, &L);
+  if (rc) return rc;
+  *bytes = L.total;
+  return GSR_OK;
+}
+
+extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                              size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                              uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                              gsr_frame_info *info_dev, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GSR_REQUIRE(g && cam && workspace && image, "null pointer");
+  GSR_REQUIRE(max_dup > 0, "max_dup must be positive");
+  FrameLayout L;
+  int rc = frame_layout(g->n, cam->width, cam->height, max_dup, &L);
+  if (rc) return rc;
+  if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+    set_error("render workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
+    return GSR_ERR_WORKSPACE_TOO_SMALL;
+  }
+  const TileGrid tg = make_grid(cam->width, cam->height);
+  if (tile_row_begin < 0) tile_row_begin = 0;
+  if (tile_row_end < 0 || tile_row_end > tg.tiles_y) tile_row_end = tg.tiles_y;
+  char *ws = (char *)workspace;
+  uint32_t *depth_key = (uint32_t *)(ws + L.depth_key), *tiles_touched = (uint32_t *)(ws + L.tiles_touched);
+  uint16_t *rect = (uint16_t *)(ws + L.rect);
+  float *rec = (float *)(ws + L.rec);
+  uint32_t *order = (uint32_t *)(ws + L.order), *blend_rank = (uint32_t *)(ws + L.blend_rank);
+  uint32_t *tile_gids = (uint32_t *)(ws + L.tile_gids), *tile_ranges = (uint32_t *)(ws + L.tile_ranges);
+  const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
+  if (info_dev) GSR_CHECK_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(gsr_frame_info), stream));
+  rc = gsr_preprocess_fwd(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, rect, rec, nullptr, nullptr,
+                          nullptr, nullptr, stream);
+  if (rc) return rc;
+  rc = gsr_bin(g->n, depth_key, tiles_touched, rect, cam->width, cam->height, max_dup, order,
+               windowed ? blend_rank : nullptr, tile_gids, tile_ranges, info_dev, ws + L.bin, L.bin_bytes, stream);
+  if (rc) return rc;
+  return gsr_blend_fwd(rec, tile_gids, tile_ranges, cam->width, cam->height, tile_row_begin, tile_row_end,
+                       windowed ? blend_rank : nullptr, first_rank, last_rank, image, final_T, n_contrib, nullptr,
+                       stream);
+}
+
+// Host-buffer frame: stands where the body of the reference's run_rasterization stands (rasterize.py:354-452).
+extern "C" int gsr_render_host(const gsr_gaussians *gh, const gsr_camera *cam, int64_t max_dup, float *image_host,
+                               gsr_frame_info *info_host) {
+  GSR_REQUIRE(gh && cam && image_host, "null pointer");
+  GSR_REQUIRE(gh->n >= 0 && max_dup > 0, "bad sizes");
+  const int64_t n = gh->n;
+  const size_t n1 = (size_t)(n > 0 ? n : 1);
+  size_t ws_bytes = 0;
+  int rc = gsr_render_workspace_bytes(n, cam->width, cam->height, max_dup, &ws_bytes);
+  if (rc) return rc;
+  const size_t img_bytes = sizeof(float) * 3 * (size_t)cam->width * cam->height;
+  // device staging: parameters are repacked on the host side only if strided; contiguous views are copied as is
+  float *d_params = nullptr, *d_image = nullptr;
+  void *d_ws = nullptr;
+  gsr_frame_info *d_info = nullptr;
+  cudaStream_t stream = nullptr;
+  const size_t param_floats = n1 * (3 + 3 + 4 + 1 + 48);
+  auto cleanup = [&]() {
+    if (d_params) cudaFree(d_params);
+    if (d_image) cudaFree(d_image);
+    if (d_ws) cudaFree(d_ws);
+    if (d_info) cudaFree(d_info);
+    if (stream) cudaStreamDestroy(stream);
+  };
+#define GSR_HOST_CHECK(expr)                                                                    \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(e__));                               \
+      cleanup();                                                                                \
+      return GSR_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+  GSR_HOST_CHECK(cudaStreamCreate(&stream));
+  GSR_HOST_CHECK(cudaMalloc(&d_params, sizeof(float) * param_floats));
+  GSR_HOST_CHECK(cudaMalloc(&d_image, img_bytes));
+  GSR_HOST_CHECK(cudaMalloc(&d_ws, ws_bytes));
+  GSR_HOST_CHECK(cudaMalloc(&d_info, sizeof(gsr_frame_info)));
+  gsr_gaussians gd = *gh;
+  float *cursor = d_params;
+  // each attribute is uploaded as the smallest host span that contains its strided view; strides are kept
+  auto upload = [&](const float *src, int64_t sn, int64_t s1, int64_t c1, int64_t s2, int64_t c2, const float **dst) -> cudaError_t {
+    int64_t span = 1 + (n1 - 1) * sn + (c1 - 1) * s1 + (c2 - 1) * s2;
+    cudaError_t e = cudaMemcpyAsync(cursor, src, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, stream);
+    *dst = cursor;
+    cursor += span;
+    return e;
+  };
+  // spans never exceed the dense element count for the layouts torch produces (contiguous or planar views)
+  GSR_HOST_CHECK(upload(gh->xyz, gh->xyz_sn, gh->xyz_sc, 3, 0, 1, &gd.xyz));
+  GSR_HOST_CHECK(upload(gh->log_scales, gh->scale_sn, gh->scale_sc, 3, 0, 1, &gd.log_scales));
+  GSR_HOST_CHECK(upload(gh->rots, gh->rot_sn, gh->rot_sc, 4, 0, 1, &gd.rots));
+  GSR_HOST_CHECK(upload(gh->opacity_logit, gh->opacity_sn, 0, 1, 0, 1, &gd.opacity_logit));
+  GSR_HOST_CHECK(upload(gh->sh, gh->sh_sn, gh->sh_sk, 16, gh->sh_sc, 3, &gd.sh));
+  if ((size_t)(cursor - d_params) > param_floats) {
+    set_error("strided host views overlap-expand beyond the dense size; pass contiguous or planar arrays");
+    cleanup();
+    return GSR_ERR_INVALID_ARGUMENT;
+  }
+  rc = gsr_render_fwd(&gd, cam, max_dup, d_ws, ws_bytes, d_image, nullptr, nullptr, 0, 0xFFFFFFFFu, 0, -1, d_info, stream);
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  GSR_HOST_CHECK(cudaMemcpyAsync(image_host, d_image, img_bytes, cudaMemcpyDeviceToHost, stream));
+  gsr_frame_info info;
+  GSR_HOST_CHECK(cudaMemcpyAsync(&info, d_info, sizeof info, cudaMemcpyDeviceToHost, stream));
+  GSR_HOST_CHECK(cudaStreamSynchronize(stream));
+  if (info_host) *info_host = info;
+  cleanup();
+  if (info.status != GSR_OK) {
+    set_error("binning produced %u (Gaussian, tile) pairs but max_dup is %lld", info.n_dup, (long long)max_dup);
+    return (int)info.status;
+  }
+  return GSR_OK;
+}

@@ -1,0 +1,245 @@
+// binning.cu - from per-Gaussian (depth key, tile rect) to per-tile, depth-ordered Gaussian lists.
+//
+// The textbook route sorts N_dup 64-bit (tile | depth) keys: ceil((32+log2 tiles)/8) = 6 radix passes over 12-byte
+// pairs.  The same total order - (tile, depth bits, Gaussian index) - is produced here with a third of the
+// traffic by sorting on the two fields separately, most significant last:
+//   1. stable sort of the N Gaussians by their 32-bit depth key (4 passes over 8-byte pairs, N << N_dup);
+//   2. walk the Gaussians in depth order, warp-shuffle prefix scan of tiles-touched with a decoupled look-back
+//      across CTAs, and emit one (tile id, Gaussian id) pair per touched tile - pairs come out depth-ordered;
+//   3. stable sort of the pairs by tile id only (ceil(log2 tiles / 8) = 2 passes at 1080p);
+//   4. mark the [begin, end) range of every tile.
+// Stability of both sorts makes ties fall back to the Gaussian index, i.e. the result is bit-identical to a
+// stable CPU sort of the 64-bit keys (tests/test_gpu_binning.py checks exactly that).
+// Replaces torch.sort at /root/reference/rasterize.py:424-425 and the implicit "for every Gaussian, for every
+// pixel of its bbox" visit order of :440-446.
+//
+// The number of pairs never travels to the host: it is left in device memory (clamped to the caller's capacity,
+// overflow flagged in gsr_frame_info.status) and every later kernel reads it from there.
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+constexpr unsigned long long kScanAggregate = 1ull << 62;
+constexpr unsigned long long kScanInclusive = 2ull << 62;
+constexpr unsigned long long kScanValue = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct BinCounters {   // device words shared by the binning kernels
+  uint32_t n_dup;      // pairs actually stored (<= capacity): the n of the tile sort and of range marking
+  uint32_t ticket;     // dynamic CTA index of scan_emit
+  uint32_t pad[2];
+};
+
+// packed scan element: low 31 bits = tiles touched, bits 31..61 = visible count
+__device__ __forceinline__ unsigned long long pack_scan(uint32_t tiles, uint32_t vis) {
+  return (unsigned long long)tiles | ((unsigned long long)vis << 31);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles_touched,
+                 const ushort4 *__restrict__ rect, int tiles_x, uint32_t capacity, unsigned long long *status,
+                 BinCounters *ctr, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids,
+                 uint32_t *__restrict__ blend_rank, gsr_frame_info *info) {
+  __shared__ unsigned long long s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t first = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
+
+  uint32_t gid[kScanItems], cnt[kScanItems];
+  unsigned long long mine = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const int64_t pos = first + j;
+    gid[j] = 0;
+    cnt[j] = 0;
+    if (pos < n) {
+      gid[j] = __ldg(order + pos);
+      cnt[j] = __ldg(tiles_touched + gid[j]);
+    }
+    mine += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
+  }
+  // warp-shuffle inclusive scan, then across warps
+  unsigned long long inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += up;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  unsigned long long pre = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < warp) pre += s_warp[w];
+    total += s_warp[w];
+  }
+  // decoupled look-back (thread 0), broadcast through shared memory
+  if (tid == 0) {
+    unsigned long long prefix = 0;
+    if (tile == 0) {
+      st_volatile_u64(status, kScanInclusive | total);
+    } else {
+      st_volatile_u64(status + tile, kScanAggregate | total);
+      const unsigned long long *look = status + tile - 1;
+      while (true) {
+        const unsigned long long v = ld_volatile_u64(look);
+        if ((v >> 62) == 0) continue;
+        prefix += v & kScanValue;
+        if (v & kScanInclusive) break;
+        --look;
+      }
+      st_volatile_u64(status + tile, kScanInclusive | (prefix + total));
+    }
+    s_base = prefix;
+    const int64_t tiles_total = (n + kScanTile - 1) / kScanTile;
+    if ((int64_t)tile == tiles_total - 1) {  // last CTA in depth order knows the totals
+      const unsigned long long all = prefix + total;
+      const uint32_t dup = (uint32_t)(all & 0x7FFFFFFFull), vis = (uint32_t)(all >> 31);
+      ctr->n_dup = dup < capacity ? dup : capacity;
+      if (info) {
+        info->n_dup = dup;
+        info->n_visible = vis;
+        if (dup > capacity) info->status = GSR_ERR_DUP_OVERFLOW;
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long run = s_base + pre + inc - mine;  // exclusive prefix of this thread's first item
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (cnt[j]) {
+      uint32_t off = (uint32_t)(run & 0x7FFFFFFFull);
+      const uint32_t vis_rank = (uint32_t)(run >> 31);
+      const ushort4 r = __ldg(rect + gid[j]);
+      if (blend_rank) blend_rank[gid[j]] = vis_rank;  // rank among the Gaussians the reference would blend
+      for (int ty = r.y; ty < r.w; ++ty)
+        for (int tx = r.x; tx < r.z; ++tx) {
+          if (off < capacity) {
+            tile_keys[off] = (uint32_t)(ty * tiles_x + tx);
+            tile_gids[off] = gid[j];
+          }
+          ++off;
+        }
+    }
+    run += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
+  }
+}
+
+__global__ void tile_ranges_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_dev,
+                                   uint2 *__restrict__ ranges) {
+  const uint32_t n = *n_dev;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = keys[i];
+    if (i == 0 || keys[i - 1] != t) ranges[t].x = i;
+    if (i == n - 1 || keys[i + 1] != t) ranges[t].y = i + 1;
+  }
+}
+
+struct BinLayout {
+  size_t counters, scan_status, depth_sort, tile_sort, dkeys_tmp, dkeys_out, dvals_tmp, tkeys_a, tkeys_b, tkeys_c,
+      tgids_a, tgids_b, total;
+};
+
+static BinLayout bin_layout(int64_t n, int64_t max_dup) {
+  BinLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  const int64_t n1 = n > 0 ? n : 1, d1 = max_dup > 0 ? max_dup : 1;
+  L.counters = take(sizeof(BinCounters));
+  L.scan_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kScanTile));
+  L.depth_sort = take(sort_scratch_bytes(n1));
+  L.tile_sort = take(sort_scratch_bytes(d1));
+  L.dkeys_tmp = take(4 * (size_t)n1);
+  L.dkeys_out = take(4 * (size_t)n1);
+  L.dvals_tmp = take(4 * (size_t)n1);
+  L.tkeys_a = take(4 * (size_t)d1);
+  L.tkeys_b = take(4 * (size_t)d1);
+  L.tkeys_c = take(4 * (size_t)d1);
+  L.tgids_a = take(4 * (size_t)d1);
+  L.tgids_b = take(4 * (size_t)d1);
+  L.total = off;
+  return L;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes) {
+  GSR_REQUIRE(bytes && n >= 0 && max_dup >= 0 && width > 0 && height > 0, "bad arguments");
+  *bytes = bin_layout(n, max_dup).total;
+  return GSR_OK;
+}
+
+extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *tiles_touched, const uint16_t *rect,
+                       int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order, uint32_t *blend_rank,
+                       uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
+                       size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GSR_REQUIRE(depth_key && tiles_touched && rect && depth_order && tile_gids && tile_ranges && workspace, "null pointer");
+  GSR_REQUIRE(n >= 0 && n < (1ll << 30) && max_dup > 0 && max_dup < (1ll << 30), "n / max_dup out of range");
+  GSR_REQUIRE(width > 0 && height > 0, "bad image size");
+  const BinLayout L = bin_layout(n, max_dup);
+  if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+    set_error("bin workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
+    return GSR_ERR_WORKSPACE_TOO_SMALL;
+  }
+  char *ws = (char *)workspace;
+  const TileGrid tg = make_grid(width, height);
+  const int num_tiles = tg.tiles_x * tg.tiles_y;
+  BinCounters *ctr = (BinCounters *)(ws + L.counters);
+  unsigned long long *scan_status = (unsigned long long *)(ws + L.scan_status);
+  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.depth_sort - L.counters, stream));  // counters + scan status
+  GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+  if (n == 0) return GSR_OK;
+
+  // 1. global depth order (ties by Gaussian index)
+  SortScratch s1, s2;
+  int rc = sort_scratch_carve(ws + L.depth_sort, L.tile_sort - L.depth_sort, n, &s1);
+  if (rc) return rc;
+  rc = launch_sort_pairs(depth_key, nullptr, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
+                         (uint32_t *)(ws + L.dvals_tmp), n, nullptr, 0, 32, s1, stream, true);
+  if (rc) return rc;
+
+  // 2. prefix scan of tiles-touched in depth order + pair emission
+  uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
+  scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, 0, stream>>>(
+      n, depth_order, tiles_touched, (const ushort4 *)rect, tg.tiles_x, (uint32_t)max_dup, scan_status, ctr, tkeys_a,
+      tgids_a, blend_rank, info_dev);
+  GSR_LAUNCH_CHECK();
+
+  // 3. stable sort of the pairs by tile id
+  int tile_bits = 1;
+  while ((1 << tile_bits) < num_tiles) ++tile_bits;
+  rc = sort_scratch_carve(ws + L.tile_sort, L.dkeys_tmp - L.tile_sort, max_dup, &s2);
+  if (rc) return rc;
+  uint32_t *tkeys_sorted = (uint32_t *)(ws + L.tkeys_c);
+  rc = launch_sort_pairs(tkeys_a, tgids_a, tkeys_sorted, tile_gids, (uint32_t *)(ws + L.tkeys_b),
+                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false);
+  if (rc) return rc;
+
+  // 4. [begin, end) of every tile
+  tile_ranges_kernel<<<148 * 8, 256, 0, stream>>>(tkeys_sorted, &ctr->n_dup, (uint2 *)tile_ranges);
+  GSR_LAUNCH_CHECK();
+  return GSR_OK;
+}

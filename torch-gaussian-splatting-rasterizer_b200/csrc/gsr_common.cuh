@@ -1,0 +1,82 @@
+// gsr_common.cuh - shared host/device plumbing for libgsr_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+// ---- error reporting across the C ABI (no exceptions) -------------------------------------------
+void set_error(const char *fmt, ...);
+#define GSR_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      gsr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return GSR_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+#define GSR_REQUIRE(cond, msg)                              \
+  do {                                                      \
+    if (!(cond)) {                                          \
+      gsr::set_error("invalid argument: %s", msg);          \
+      return GSR_ERR_INVALID_ARGUMENT;                      \
+    }                                                       \
+  } while (0)
+#define GSR_LAUNCH_CHECK() GSR_CHECK_CUDA(cudaGetLastError())
+
+// ---- single-rounding float ops ---------------------------------------------------------------
+// Decisions downstream (depth order, ceil of the radius, floor of the tile rect, alpha > 1/255) are
+// discontinuous, so the geometry follows the reference's torch-CPU arithmetic operation by operation
+// (SURVEY.md App. B.8).  These intrinsics are never contracted into FMAs by nvcc.
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __fdiv_rn(1.0f, a); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+// order-preserving u32 image of an f32 (ascending)
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tile grid.  tiles_x/tiles_y cover every pixel; *_eff is the part the reference can ever write:
+// pixel column W-1 and row H-1 are never written, so a tile whose first column is >= W-1
+// can hold no Gaussian.
+struct TileGrid {
+  int tiles_x, tiles_y, tiles_x_eff, tiles_y_eff;
+};
+__host__ __device__ __forceinline__ TileGrid make_grid(int width, int height) {
+  TileGrid g;
+  g.tiles_x = ceil_div(width, GSR_TILE);
+  g.tiles_y = ceil_div(height, GSR_TILE);
+  g.tiles_x_eff = ceil_div(width - 1, GSR_TILE);
+  g.tiles_y_eff = ceil_div(height - 1, GSR_TILE);
+  return g;
+}
+
+// ---- stage launchers shared between translation units ------------------------------------------
+struct SortScratch {   // carved from a caller workspace
+  uint32_t *hist;      // [4][256] global digit counts
+  uint32_t *status;    // [passes][tiles][256] decoupled look-back state
+  uint32_t *tickets;   // [4] dynamic block ids
+  size_t status_stride;  // elements per pass
+};
+size_t sort_scratch_bytes(int64_t n);
+// zeroes and carves; returns GSR_OK or error
+int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *out);
+int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
+                      uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
+                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys);
+
+}  // namespace gsr

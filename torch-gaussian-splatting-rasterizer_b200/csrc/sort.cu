@@ -1,0 +1,267 @@
+// sort.cu - stable least-significant-digit radix sort of (u32 key, u32 value) pairs, written for sm_100a.
+//
+// Design (one-sweep): ONE histogram kernel counts every 8-bit digit of every pass up front; each pass is then a
+// single kernel in which a CTA ranks a 4096-pair tile in shared memory and learns the number of equal-digit
+// pairs in all preceding tiles through a decoupled look-back over per-tile status words (no scan kernel, one
+// read and one write of the data per pass).  CTAs take their tile index from an atomic ticket, so every tile a
+// CTA waits on belongs to a CTA that is already resident: the look-back cannot dead-lock.
+//
+// Stability + determinism: ranks are assigned in memory order (warp-major, item, lane) from counts only, so the
+// output is THE stable sort of the input whatever the scheduling - ties between equal depths keep ascending
+// Gaussian index, which is what "bit-exact against a stable CPU sort" asks for (replaces torch.sort at
+// /root/reference/rasterize.py:424-425).
+//
+// n may live on the device (n_dev): grids are sized for the capacity and surplus CTAs retire immediately, so the
+// binning stage never synchronises with the host to learn the number of (Gaussian, tile) pairs.
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per CTA
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 4;
+
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- digit histograms of all passes, one read of the keys --------------------------------------------------
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n_host,
+                                                         const uint32_t *__restrict__ n_dev,
+                                                         uint32_t *__restrict__ hist, int begin_bit, int passes,
+                                                         uint32_t last_mask) {
+  __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+  for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&s_hist[0][0])[k] = 0;
+  __syncthreads();
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int lane = threadIdx.x & 31;
+  // every warp runs the same trip count so that __match_any_sync sees full warps
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+    const int64_t i = base + lane;
+    const bool live = i < n;
+    const uint32_t key = live ? keys[i] : 0u;
+    for (int p = 0; p < passes; ++p) {
+      uint32_t d = (key >> (begin_bit + 8 * p)) & 255u;
+      if (p == passes - 1) d &= last_mask;
+      const uint32_t code = live ? d : 256u;  // dead lanes form their own group
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, code);
+      if (live && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < passes * kRadix; k += blockDim.x) {
+    const uint32_t v = (&s_hist[0][0])[k];
+    if (v) atomicAdd(&hist[k], v);
+  }
+}
+
+// exclusive scan of one value per thread over a 256-thread CTA (two values at once)
+__device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*[8]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2 inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t ax = __shfl_up_sync(0xFFFFFFFFu, inc.x, o), ay = __shfl_up_sync(0xFFFFFFFFu, inc.y, o);
+    if (lane >= o) {
+      inc.x += ax;
+      inc.y += ay;
+    }
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint2 pre = make_uint2(0, 0);
+  for (int w = 0; w < warp; ++w) {
+    pre.x += s_warp[w].x;
+    pre.y += s_warp[w].y;
+  }
+  __syncthreads();
+  return make_uint2(pre.x + inc.x - v.x, pre.y + inc.y - v.y);
+}
+
+// ---- one pass -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
+                const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
+                uint32_t *ticket, int shift, uint32_t mask) {
+  __shared__ uint32_t s_hist[kSortThreads / 32][kRadix];  // per-warp digit counts, then exclusive over warps
+  __shared__ uint32_t s_excl[kRadix];                     // first tile-local slot of each digit
+  __shared__ uint32_t s_gbase[kRadix];                    // global slot of a digit's first pair minus s_excl
+  __shared__ uint32_t s_keys[kSortTile];
+  __shared__ uint32_t s_vals[kSortTile];
+  __shared__ uint2 s_scan[kSortThreads / 32];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) (&s_hist[0][0])[k] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int64_t num_tiles = (n + kSortTile - 1) / kSortTile;
+  if ((int64_t)tile >= num_tiles) return;
+
+  // ---- load: warp w owns the contiguous run [w*512, (w+1)*512) of the tile, item i of lane l at i*32+l ----
+  const int64_t base = (int64_t)tile * kSortTile + warp * (kSortItems * 32) + lane;
+  uint32_t key[kSortItems], val[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t idx = base + i * 32;
+    const bool live = idx < n;
+    key[i] = live ? __ldg(keys_in + idx) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
+    val[i] = live ? (vals_in ? __ldg(vals_in + idx) : (uint32_t)idx) : 0u;
+  }
+
+  // ---- rank inside the warp, in (item, lane) order ----
+  uint16_t rank[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t d = (key[i] >> shift) & mask;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t before = 0;
+    if (lane == leader) before = s_hist[warp][d];
+    before = __shfl_sync(0xFFFFFFFFu, before, leader);
+    rank[i] = (uint16_t)(before + __popc(peers & ((1u << lane) - 1u)));
+    if (lane == leader) s_hist[warp][d] = before + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- thread d owns digit d: counts over warps -> exclusive, tile count, look-back ----
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w) {
+    const uint32_t c = s_hist[w][tid];
+    s_hist[w][tid] = count;
+    count += c;
+  }
+  const uint2 ex = block_exclusive_scan2(make_uint2(count, __ldg(hist + tid)), s_scan);
+  s_excl[tid] = ex.x;
+
+  uint32_t prefix = 0;
+  uint32_t *my_status = status + (size_t)tile * kRadix + tid;
+  if (tile == 0) {
+    st_volatile_u32(my_status, kFlagInclusive | count);
+  } else {
+    st_volatile_u32(my_status, kFlagAggregate | count);
+    const uint32_t *look = my_status - kRadix;
+    while (true) {
+      const uint32_t v = ld_volatile_u32(look);
+      if ((v >> 30) == 0) continue;  // predecessor has not published yet
+      prefix += v & kValueMask;
+      if (v & kFlagInclusive) break;
+      look -= kRadix;
+    }
+    st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
+  }
+  s_gbase[tid] = ex.y + prefix - ex.x;
+  __syncthreads();
+
+  // ---- scatter to the tile-local sorted position, then write runs of equal digits coalesced ----
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t d = (key[i] >> shift) & mask;
+    const uint32_t pos = s_excl[d] + s_hist[warp][d] + rank[i];
+    s_keys[pos] = key[i];
+    s_vals[pos] = val[i];
+  }
+  __syncthreads();
+  const int64_t remaining = n - (int64_t)tile * kSortTile;
+  const int valid = remaining < kSortTile ? (int)remaining : kSortTile;
+  for (int j = tid; j < valid; j += kSortThreads) {
+    const uint32_t k = s_keys[j];
+    const uint32_t dst = s_gbase[(k >> shift) & mask] + j;
+    if (keys_out) keys_out[dst] = k;
+    vals_out[dst] = s_vals[j];
+  }
+}
+
+size_t sort_scratch_bytes(int64_t n) {
+  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kSortTile);
+  return align_up(sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * tiles * kRadix), 256);
+}
+
+int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *out) {
+  if (bytes < sort_scratch_bytes(n) || ((uintptr_t)workspace & 15)) {
+    set_error("sort workspace too small or misaligned (%zu < %zu)", bytes, sort_scratch_bytes(n));
+    return GSR_ERR_WORKSPACE_TOO_SMALL;
+  }
+  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kSortTile);
+  uint32_t *p = (uint32_t *)workspace;
+  out->hist = p;
+  out->tickets = p + kMaxPasses * kRadix;
+  out->status = p + kMaxPasses * kRadix + 8;
+  out->status_stride = (size_t)tiles * kRadix;
+  return GSR_OK;
+}
+
+int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
+                      uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
+                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys) {
+  GSR_REQUIRE(n >= 0 && n < (1ll << 30), "sort size out of range (must be < 2^30)");
+  GSR_REQUIRE(begin_bit >= 0 && end_bit <= 32 && end_bit > begin_bit, "bad bit range");
+  GSR_REQUIRE(keys_in && keys_out && values_out && keys_tmp && values_tmp, "null sort buffer");
+  if (n == 0) return GSR_OK;
+  const int bits = end_bit - begin_bit;
+  const int passes = (bits + 7) / 8;
+  const int last_bits = bits - 8 * (passes - 1);
+  const uint32_t last_mask = (1u << last_bits) - 1u;
+  const int64_t tiles = ceil_div64(n, kSortTile);
+  const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
+  GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
+  {
+    int64_t want = ceil_div64(n, 256 * 8);
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    radix_hist_kernel<<<blocks, 256, 0, stream>>>(keys_in, n, n_dev, s.hist, begin_bit, passes, last_mask);
+    GSR_LAUNCH_CHECK();
+  }
+  const uint32_t *kin = keys_in, *vin = values_in;
+  for (int p = 0; p < passes; ++p) {
+    const bool to_out = ((passes - 1 - p) % 2) == 0;
+    uint32_t *kout = to_out ? keys_out : keys_tmp;
+    uint32_t *vout = to_out ? values_out : values_tmp;
+    if (p == passes - 1 && skip_final_keys) kout = nullptr;  // caller only wants the permutation
+    const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
+    onesweep_kernel<<<(unsigned)tiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, s.hist + p * kRadix,
+                                                                  s.status + p * s.status_stride, s.tickets + p,
+                                                                  begin_bit + 8 * p, mask);
+    GSR_LAUNCH_CHECK();
+    kin = kout;
+    vin = vout;
+  }
+  return GSR_OK;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" int gsr_sort_workspace_bytes(int64_t n, size_t *bytes) {
+  GSR_REQUIRE(bytes && n >= 0, "bad arguments");
+  *bytes = sort_scratch_bytes(n);
+  return GSR_OK;
+}
+
+extern "C" int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out,
+                              uint32_t *values_out, uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n,
+                              const uint32_t *n_dev, int32_t begin_bit, int32_t end_bit, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+  SortScratch s;
+  int rc = sort_scratch_carve(workspace, workspace_bytes, n, &s);
+  if (rc) return rc;
+  return launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, n_dev, begin_bit,
+                           end_bit, s, (cudaStream_t)stream, false);
+}

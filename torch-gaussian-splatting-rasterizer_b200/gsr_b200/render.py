@@ -1,0 +1,263 @@
+"""Host side of the B200 render path: device containers, workspace management and the ``render`` calls.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only; every per-Gaussian or
+per-pixel operation happens in libgsr_b200.so through the C ABI (``_cabi``).  The reference inlines this whole
+path in its click command (/root/reference/rasterize.py:347-452); ``render`` is that body as a function.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .camera import CameraStruct, make_camera
+
+U32_MAX = 0xFFFFFFFF
+
+
+# ----------------------------------------------------------------------------------------------
+# device container
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class GaussianModel:
+    """Raw 3DGS parameters resident in HBM.
+
+    Layout (DESIGN.md "Data layout"): xyz [N,3], log_scales [N,3], rots [N,4], opacity [N] contiguous; SH as the
+    planar block [3,16,N] the reference itself builds (utils.py:21-31), exposed as its [N,16,3] view - with it
+    every load instruction of a warp in the preprocess kernel reads one full 128-byte line.
+    """
+
+    xyz: torch.Tensor
+    log_scales: torch.Tensor
+    rots: torch.Tensor
+    opacity: torch.Tensor
+    sh: torch.Tensor  # logical [N,16,3], any strides
+
+    @property
+    def n(self) -> int:
+        return int(self.xyz.shape[0])
+
+    @property
+    def device(self):
+        return self.xyz.device
+
+    @staticmethod
+    def from_tensors(means, log_scales, quats, opacity_logits, sh, device="cuda", planar_sh: bool = True,
+                     non_blocking: bool = False) -> "GaussianModel":
+        def up(t, shape):
+            t = torch.as_tensor(t)
+            if t.dtype != torch.float32:
+                t = t.float()
+            assert tuple(t.shape[1:]) == shape, (t.shape, shape)
+            return t.to(device, non_blocking=non_blocking)
+
+        sh = torch.as_tensor(sh)
+        assert sh.dim() == 3 and tuple(sh.shape[1:]) == (16, 3), "sh must be [N,16,3]"
+        sh = sh.float() if sh.dtype != torch.float32 else sh
+        sh_d = sh.to(device, non_blocking=non_blocking)  # keeps the strides of the source (planar stays planar)
+        if planar_sh and sh_d.stride() != (1, sh_d.shape[0], 16 * sh_d.shape[0]):
+            sh_d = sh_d.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+        op = torch.as_tensor(opacity_logits).float().reshape(-1).to(device, non_blocking=non_blocking)
+        return GaussianModel(up(means, (3,)), up(log_scales, (3,)), up(quats, (4,)), op, sh_d)
+
+    @staticmethod
+    def from_cloud(cloud, device="cuda") -> "GaussianModel":
+        """From a host ``scenes.GaussianCloud`` (PLY columns)."""
+        sh = torch.from_numpy(cloud.sh_planar()).permute(2, 1, 0)  # [N,16,3] view of planar storage
+        return GaussianModel.from_tensors(torch.from_numpy(cloud.xyz), torch.from_numpy(cloud.scales),
+                                          torch.from_numpy(cloud.rots), torch.from_numpy(cloud.opacity), sh, device)
+
+    def c_struct(self) -> _cabi.Gaussians:
+        g = _cabi.Gaussians()
+        g.n = self.n
+        for name, t in (("xyz", self.xyz), ("log_scales", self.log_scales), ("rots", self.rots)):
+            assert t.dtype == torch.float32 and t.is_cuda
+            setattr(g, name, t.data_ptr())
+        g.xyz_sn, g.xyz_sc = self.xyz.stride()
+        g.scale_sn, g.scale_sc = self.log_scales.stride()
+        g.rot_sn, g.rot_sc = self.rots.stride()
+        g.opacity_logit, g.opacity_sn = self.opacity.data_ptr(), self.opacity.stride(0)
+        g.sh = self.sh.data_ptr()
+        g.sh_sn, g.sh_sk, g.sh_sc = self.sh.stride()
+        return g
+
+
+def _align256(t: torch.Tensor) -> torch.Tensor:
+    off = (-t.data_ptr()) % 256
+    return t[off:]
+
+
+class Renderer:
+    """Owns the workspace for frames of one size class and enqueues whole frames on the current stream."""
+
+    def __init__(self, device="cuda", dup_factor: float = 8.0):
+        _cabi.require_cuda()
+        self.device = torch.device(device)
+        self.dup_factor = dup_factor
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_key = None
+        self.max_dup = 0
+        self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)  # gsr_frame_info (32 bytes)
+
+    # -- workspace ---------------------------------------------------------------------------
+    def reserve(self, n: int, width: int, height: int, max_dup: Optional[int] = None) -> None:
+        max_dup = int(max_dup if max_dup is not None else max(self.max_dup, self.dup_factor * n, 1 << 16))
+        max_dup = min(max_dup, (1 << 30) - 1)
+        key = (n, width, height, max_dup)
+        if self._ws is not None and self._ws_key == key:
+            return
+        need = ctypes.c_size_t()
+        _cabi.call("gsr_render_workspace_bytes", n, width, height, max_dup, ctypes.byref(need))
+        if self._ws is None or self._ws.numel() < need.value + 256:
+            self._ws = None
+            self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
+        self._ws_key, self.max_dup = key, max_dup
+
+    # -- one frame ---------------------------------------------------------------------------
+    def render(self, model: GaussianModel, cam: CameraStruct, out: Optional[torch.Tensor] = None,
+               final_T: Optional[torch.Tensor] = None, n_contrib: Optional[torch.Tensor] = None,
+               first_rank: int = 0, last_rank: int = U32_MAX, tile_rows: Optional[Sequence[int]] = None,
+               check: bool = True) -> torch.Tensor:
+        """Enqueue one frame; returns image ``[H,W,3]`` float32 (the reference's ``screen.transpose(1,0)``)."""
+        W, H = cam.width, cam.height
+        self.reserve(model.n, W, H)
+        if out is None:
+            out = torch.empty((H, W, 3), dtype=torch.float32, device=self.device)
+        assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (H, W, 3)
+        rb, re = (0, -1) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+        while True:
+            ws = _align256(self._ws)
+            g = model.c_struct()
+            _cabi.call("gsr_render_fwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws),
+                       ws.numel(), _cabi.ptr(out), _cabi.ptr(final_T), _cabi.ptr(n_contrib), first_rank, last_rank,
+                       rb, re, _cabi.ptr(self.info_dev), _cabi.stream_handle())
+            if not check:
+                return out
+            info = self.frame_info()
+            if info["status"] == _cabi.GSR_ERR_DUP_OVERFLOW:  # grow once to the exact need and redo the frame
+                self.reserve(model.n, W, H, max_dup=int(info["n_dup"] * 1.1) + 1024)
+                continue
+            if info["status"] != _cabi.GSR_OK:
+                raise _cabi.GsrError(info["status"], "frame failed")
+            return out
+
+    def frame_info(self) -> Dict[str, int]:
+        """Synchronising read-back of the last frame's counters."""
+        raw = self.info_dev.cpu().numpy().view(np.uint32)
+        return dict(status=int(raw[0]), n_visible=int(raw[1]), n_dup=int(raw[2]),
+                    warp_evals=int(raw[4]) | (int(raw[5]) << 32), pixel_evals=int(raw[6]) | (int(raw[7]) << 32))
+
+
+_default_renderer: Optional[Renderer] = None
+
+
+def default_renderer() -> Renderer:
+    global _default_renderer
+    if _default_renderer is None:
+        _default_renderer = Renderer()
+    return _default_renderer
+
+
+def render(means, log_scales, quats, opacity_logits, sh, qvec, tvec, fx, fy, cam_width, cam_height, width, height,
+           degree: int = 3, renderer: Optional[Renderer] = None) -> torch.Tensor:
+    """The reference's render path as a function (rasterize.py:347-452).
+
+    Tensors may live on the host (they are uploaded - this is the end-to-end path the benchmark's ``e2e`` times)
+    or on the GPU.  Returns the ``[H,W,3]`` float32 image on the GPU; no background term, black where nothing
+    was blended, last row / column zero like the reference.
+    """
+    _cabi.require_cuda()
+    r = renderer or default_renderer()
+    model = GaussianModel.from_tensors(means, log_scales, quats, opacity_logits, sh, device=r.device)
+    cam = make_camera(qvec, tvec, fx, fy, cam_width, cam_height, width, height, degree)
+    return r.render(model, cam)
+
+
+def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: Optional[Renderer] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Render a list of ``scenes.View`` with one resident model: ``[V,H,W,3]`` (video / orbit path)."""
+    from .camera import camera_for
+
+    r = renderer or default_renderer()
+    if out is None:
+        out = torch.empty((len(views), intr.height, intr.width, 3), dtype=torch.float32, device=r.device)
+    for i, v in enumerate(views):
+        r.render(model, camera_for(intr, v, degree), out=out[i], check=(i == len(views) - 1))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# stage-level wrappers (tests and profiling drive the stages one by one)
+# ----------------------------------------------------------------------------------------------
+def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, tile_rows=None) -> Dict[str, torch.Tensor]:
+    _cabi.require_cuda()
+    n, dev = model.n, model.device
+    rb, re = (0, 1 << 30) if tile_rows is None else tile_rows
+    out = dict(depth_key=torch.empty(n, dtype=torch.int32, device=dev),
+               tiles_touched=torch.empty(n, dtype=torch.int32, device=dev),
+               rect=torch.empty((n, 4), dtype=torch.int16, device=dev),
+               rec=torch.zeros((n, _cabi.REC_FLOATS), dtype=torch.float32, device=dev))
+    if debug:
+        out.update(cov3d=torch.empty((n, 3, 3), dtype=torch.float32, device=dev),
+                   cov2d=torch.empty((n, 2, 2), dtype=torch.float32, device=dev),
+                   tile_rect=torch.empty((n, 4), dtype=torch.int32, device=dev),
+                   mean2d=torch.empty((n, 2), dtype=torch.float32, device=dev))
+    g = model.c_struct()
+    _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), rb, re, _cabi.ptr(out["depth_key"]),
+               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["rect"]), _cabi.ptr(out["rec"]),
+               _cabi.ptr(out.get("cov3d")), _cabi.ptr(out.get("cov2d")), _cabi.ptr(out.get("tile_rect")),
+               _cabi.ptr(out.get("mean2d")), _cabi.stream_handle())
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, values: Optional[torch.Tensor], begin_bit: int = 0, end_bit: int = 32,
+               n_dev: Optional[torch.Tensor] = None):
+    _cabi.require_cuda()
+    n = keys.numel()
+    need = ctypes.c_size_t()
+    _cabi.call("gsr_sort_workspace_bytes", n, ctypes.byref(need))
+    ws = _align256(torch.empty(need.value + 256, dtype=torch.uint8, device=keys.device))
+    ko, vo, kt, vt = (torch.empty_like(keys) for _ in range(4))
+    _cabi.call("gsr_sort_pairs", _cabi.ptr(keys), _cabi.ptr(values), _cabi.ptr(ko), _cabi.ptr(vo), _cabi.ptr(kt),
+               _cabi.ptr(vt), n, _cabi.ptr(n_dev), begin_bit, end_bit, _cabi.ptr(ws), ws.numel(), _cabi.stream_handle())
+    return ko, vo
+
+
+def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: int) -> Dict[str, torch.Tensor]:
+    _cabi.require_cuda()
+    dev = pre["depth_key"].device
+    n = pre["depth_key"].numel()
+    tiles = ((width + 15) // 16) * ((height + 15) // 16)
+    need = ctypes.c_size_t()
+    _cabi.call("gsr_bin_workspace_bytes", n, width, height, max_dup, ctypes.byref(need))
+    ws = _align256(torch.empty(need.value + 256, dtype=torch.uint8, device=dev))
+    out = dict(order=torch.empty(n, dtype=torch.int32, device=dev),
+               blend_rank=torch.zeros(n, dtype=torch.int32, device=dev),
+               tile_gids=torch.empty(max_dup, dtype=torch.int32, device=dev),
+               tile_ranges=torch.empty((tiles, 2), dtype=torch.int32, device=dev),
+               info=torch.zeros(8, dtype=torch.int32, device=dev))
+    _cabi.call("gsr_bin", n, _cabi.ptr(pre["depth_key"]), _cabi.ptr(pre["tiles_touched"]), _cabi.ptr(pre["rect"]),
+               width, height, max_dup, _cabi.ptr(out["order"]), _cabi.ptr(out["blend_rank"]),
+               _cabi.ptr(out["tile_gids"]), _cabi.ptr(out["tile_ranges"]), _cabi.ptr(out["info"]), _cabi.ptr(ws),
+               ws.numel(), _cabi.stream_handle())
+    out["_ws"] = ws
+    return out
+
+
+def blend(pre, binned, width: int, height: int, count: bool = False, first_rank: int = 0, last_rank: int = U32_MAX,
+          tile_rows=None):
+    _cabi.require_cuda()
+    dev = pre["rec"].device
+    image = torch.empty((height, width, 3), dtype=torch.float32, device=dev)
+    final_T = torch.empty((height, width), dtype=torch.float32, device=dev)
+    n_contrib = torch.empty((height, width), dtype=torch.int32, device=dev)
+    info = torch.zeros(8, dtype=torch.int32, device=dev) if count else None
+    rb, re = (0, -1) if tile_rows is None else tile_rows
+    _cabi.call("gsr_blend_fwd", _cabi.ptr(pre["rec"]), _cabi.ptr(binned["tile_gids"]), _cabi.ptr(binned["tile_ranges"]),
+               width, height, rb, re, _cabi.ptr(binned.get("blend_rank")), first_rank, last_rank, _cabi.ptr(image),
+               _cabi.ptr(final_T), _cabi.ptr(n_contrib), _cabi.ptr(info), _cabi.stream_handle())
+    return dict(image=image, final_T=final_T, n_contrib=n_contrib, info=info)
