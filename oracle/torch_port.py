@@ -119,23 +119,28 @@ def preprocess(xyz, log_scales, rots, opacity_logit, sh, cam) -> Dict[str, torch
 
 def blend_step(g: int, pre, screen, T, functional: bool):
     """rasterize.py:255-305 on the rectangular slice of the x-major screen covered by Gaussian g."""
-    x0, y0, x1, y1 = (int(v) for v in pre["pixel_bbox"][g])
+    x0, y0, x1, y1 = pre["pixel_bbox"][g].tolist()
     a, c, b = pre["conic"][g]
     dx = (pre["mean2d"][g, 0] - torch.arange(x0, x1))[:, None]
     dy = (pre["mean2d"][g, 1] - torch.arange(y0, y1))[None, :]
     power = -0.5 * (a * dx * dx + c * dy * dy) - b * dx * dy
     alpha = torch.clamp_max(pre["opacity"][g] * torch.exp(power), 0.99)
     keep = (alpha > 1 / 255) & (power <= 0)
-    alpha = torch.where(keep, alpha, torch.zeros_like(alpha))
-    t_old = T[x0:x1, y0:y1]
-    add = (alpha[:, :, None] * pre["rgb"][g]) * t_old[:, :, None]
-    if functional:
+    if functional:  # autograd-friendly: dense update of the slice on fresh copies
+        alpha = torch.where(keep, alpha, torch.zeros_like(alpha))
+        t_old = T[x0:x1, y0:y1]
+        add = (alpha[:, :, None] * pre["rgb"][g]) * t_old[:, :, None]
         screen = screen.clone(); T = T.clone()
         screen[x0:x1, y0:y1] = screen[x0:x1, y0:y1] + add
         T[x0:x1, y0:y1] = t_old * (1 - alpha)
-    else:
-        screen[x0:x1, y0:y1] += add
-        t_old *= (1 - alpha)
+        return screen, T
+    # timing path: touch only the pixels that pass the test, in place, like the reference's masked update
+    ix, iy = torch.nonzero(keep, as_tuple=True)
+    ix += x0; iy += y0
+    av = alpha[keep]
+    tv = T[ix, iy]
+    screen[ix, iy] += (av[:, None] * pre["rgb"][g]) * tv[:, None]
+    T[ix, iy] = tv * (1 - av)
     return screen, T
 
 
