@@ -72,9 +72,9 @@ typedef struct gsr_frame_info {
 
 /* Per-Gaussian record consumed by the blend kernel: 3 x float4, 16-byte aligned. */
 #define GSR_REC_FLOATS 12
-/*  [0] mean2d.x  [1] mean2d.y  [2] conic a  [3] conic c      (sigmas = (a, c, b), rasterize.py:404-411)
- *  [4] conic b   [5] opacity   [6] r        [7] g
- *  [8] b(lue)    [9] depth z   [10] radius  [11] 0                                                   */
+/*  [0] mean2d.x  [1] mean2d.y  [2] A = -a/2   [3] C = -c/2     (a, c, b) = sigmas, rasterize.py:404-411
+ *  [4] B = -b    [5] thr       [6] opacity    [7] r            power = (A dx^2 + C dy^2) + (B dx) dy
+ *  [8] g         [9] b(lue)    [10] depth z   [11] radius      thr = -ln(255 opacity) - 1e-4: alpha <= 1/255 below it */
 
 const char *gsr_last_error(void);
 int gsr_abi_version(void);

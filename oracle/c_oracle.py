@@ -73,6 +73,11 @@ def blend(pre: Dict[str, np.ndarray], order: np.ndarray, width: int, height: int
     screen = np.zeros((width, height, 3), np.float32)
     T = np.ones((width, height), np.float32)
     last = order.shape[0] if last is None else last
+    c = np.ascontiguousarray  # fixtures loaded from .npz may be Fortran-ordered
+    order = c(order, dtype=np.int64)
+    pre = dict(skip=c(pre["skip"], dtype=np.uint8), pixel_bbox=c(pre["pixel_bbox"], dtype=np.int32),
+               mean2d=c(pre["mean2d"], dtype=np.float32), conic=c(pre["conic"], dtype=np.float32),
+               rgb=c(pre["rgb"], dtype=np.float32), opacity=c(pre["opacity"], dtype=np.float32))
     nb = lib().gsr_oracle_blend(
         ctypes.c_int64(order.shape[0]), _p(order), _p(pre["skip"]), _p(pre["pixel_bbox"]), _p(pre["mean2d"]),
         _p(pre["conic"]), _p(pre["rgb"]), _p(pre["opacity"]), ctypes.c_int(width), ctypes.c_int(height),

@@ -48,15 +48,16 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     rec = pre["rec"]
     # bit-exact against the reference itself (no exp involved)
     assert np.array_equal(_bits(pre["mean2d"]), _bits(g["mean2d"]))
-    assert np.array_equal(_bits(rec[:, 9]), _bits(g["depth"]))
-    assert np.array_equal(_bits(rec[:, 6:9]), _bits(g["rgb"]))
-    assert np.array_equal(_bits(rec[:, 5]), _bits(g["opacity"]))
+    assert np.array_equal(_bits(rec[:, 10]), _bits(g["depth"]))
+    assert np.array_equal(_bits(rec[:, 7:10]), _bits(g["rgb"]))
+    assert np.array_equal(_bits(rec[:, 6]), _bits(g["opacity"]))
     assert np.array_equal(pre["tile_rect"], g["tile_rect"])
     # bit-exact against the oracle (same exp recipes)
     assert np.array_equal(_bits(pre["cov3d"]), _bits(o["cov3d"]))
     assert np.array_equal(_bits(pre["cov2d"]), _bits(o["cov2d"]))
-    assert np.array_equal(_bits(rec[:, [2, 3, 4]]), _bits(o["conic"]))
-    assert np.array_equal(_bits(rec[:, 10]), _bits(o["radius"]))
+    conic = np.stack([-2 * rec[:, 2], -2 * rec[:, 3], -rec[:, 4]], axis=1)  # record stores (-a/2, -c/2, -b)
+    assert np.array_equal(_bits(conic), _bits(o["conic"]))
+    assert np.array_equal(_bits(rec[:, 11]), _bits(o["radius"]))
     # exp-derived quantities agree with the reference to its own exp noise
     assert np.abs(pre["cov2d"] - g["cov2d"]).max() <= 2e-5 * np.abs(g["cov2d"]).max()
     # depth keys are an order-preserving image of the depths

@@ -120,24 +120,47 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
     }
   }
   __syncthreads();
-  unsigned long long run = s_base + pre + inc - mine;  // exclusive prefix of this thread's first item
+  // ---- warp-cooperative emission: the 128 Gaussians of a warp own one contiguous output range; lanes walk it
+  //      element by element (coalesced 128-byte stores) and find their Gaussian by binary search ----
+  __shared__ uint32_t s_off[kScanThreads / 32][32 * kScanItems + 1];
+  __shared__ uint32_t s_gid[kScanThreads / 32][32 * kScanItems];
+  __shared__ ushort4 s_rect[kScanThreads / 32][32 * kScanItems];
+  const unsigned long long thread_excl = s_base + pre + inc - mine;  // exclusive prefix of this thread's first item
+  const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, thread_excl, 0);
+  const uint32_t warp_out = (uint32_t)(warp_excl & 0x7FFFFFFFull);
+  {
+    unsigned long long run = thread_excl;
 #pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
-    if (cnt[j]) {
-      uint32_t off = (uint32_t)(run & 0x7FFFFFFFull);
-      const uint32_t vis_rank = (uint32_t)(run >> 31);
-      const ushort4 r = __ldg(rect + gid[j]);
-      if (blend_rank) blend_rank[gid[j]] = vis_rank;  // rank among the Gaussians the reference would blend
-      for (int ty = r.y; ty < r.w; ++ty)
-        for (int tx = r.x; tx < r.z; ++tx) {
-          if (off < capacity) {
-            tile_keys[off] = (uint32_t)(ty * tiles_x + tx);
-            tile_gids[off] = gid[j];
-          }
-          ++off;
-        }
+    for (int j = 0; j < kScanItems; ++j) {
+      const int slot = lane * kScanItems + j;
+      s_off[warp][slot] = (uint32_t)(run & 0x7FFFFFFFull) - warp_out;
+      s_gid[warp][slot] = gid[j];
+      if (cnt[j]) {
+        s_rect[warp][slot] = __ldg(rect + gid[j]);
+        if (blend_rank) blend_rank[gid[j]] = (uint32_t)(run >> 31);  // rank among the Gaussians the reference would blend
+      }
+      run += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
     }
-    run += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
+    if (lane == 31) s_off[warp][32 * kScanItems] = (uint32_t)(run & 0x7FFFFFFFull) - warp_out;
+  }
+  __syncwarp();
+  const uint32_t warp_total = s_off[warp][32 * kScanItems];
+  for (uint32_t e = lane; e < warp_total; e += 32) {
+    int lo = 0, hi = 32 * kScanItems;  // last slot with s_off[slot] <= e
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[warp][mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    const ushort4 r = s_rect[warp][lo];
+    const uint32_t local = e - s_off[warp][lo];
+    const uint32_t w = (uint32_t)(r.z - r.x);
+    const uint32_t row = local / w, col = local - row * w;
+    const uint32_t out = warp_out + e;
+    if (out < capacity) {
+      tile_keys[out] = (r.y + row) * (uint32_t)tiles_x + r.x + col;
+      tile_gids[out] = s_gid[warp][lo];
+    }
   }
 }
 

@@ -14,86 +14,172 @@
 // takes T below 1e-4 (what is left can change the colour by < 1e-4; stopping before that blend, as 3DGS does,
 // measured 4.7e-3 - SURVEY.md Q12).  Pixel column W-1 and row H-1 are never written by the reference (Q8).
 //
-// Work decomposition: one CTA per tile, one thread per pixel; the tile's list is staged through shared memory
-// in batches of 256 records (each thread gathers one 48-byte record), all threads then walk the batch with
-// broadcast shared-memory reads.  A CTA leaves as soon as every pixel has terminated.
+// Work decomposition: one CTA per tile, 256/PX threads, PX pixels of one column per thread (rows rg*PX..rg*PX+PX-1),
+// so the dx-dependent half of `power` (dx, dx^2, A dx^2, B dx) is computed once per Gaussian and thread.  The tile's
+// list is staged through shared memory in batches of 128 raw 48-byte records with cp.async (LDGSTS), double
+// buffered: the gather of batch b+1 and the index loads of batch b+2 are in flight while batch b is evaluated with
+// broadcast shared-memory reads.  ~90 % of evaluations end at the `power < thr` test (6 floats read per Gaussian and
+// thread, 7 FP32 operations per pixel, no exp).  A CTA leaves as soon as every pixel has terminated; a terminated
+// pixel is parked at y = 1e18 so that it fails the test without costing an extra instruction.
+#include <stdlib.h>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
 
-constexpr int kBlendThreads = GSR_TILE * GSR_TILE;
 constexpr float kMinAlpha = (float)(1.0 / 255.0);   // MIN_ALPHA, rasterize.py:38 (compared in f32 like torch does)
 constexpr float kMaxDensity = 0.99f;                // MAX_GAUSSIAN_DENSITY, rasterize.py:36
 constexpr float kStopT = 1e-4f;
+constexpr float kParkedY = 1e18f;
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlendThreads)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int PX, bool COUNT, bool RANKED>
+__global__ void __launch_bounds__(256 / PX)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
              uint32_t *__restrict__ n_contrib, gsr_frame_info *info) {
-  __shared__ float4 s_a[kBlendThreads];  // mean.x mean.y conic.a conic.c
-  __shared__ float4 s_b[kBlendThreads];  // conic.b opacity r g
-  __shared__ float s_c[kBlendThreads];   // b
+  constexpr int THREADS = 256 / PX;
+  constexpr int kBatch = PX >= 8 ? 64 : 128;  // records per staged batch (smaller CTAs keep more CTAs resident)
+  constexpr int PER = kBatch / THREADS;  // records gathered per thread and batch
+  __shared__ __align__(16) float s_rec[2][kBatch * GSR_REC_FLOATS];
 
   const int tid = threadIdx.x;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
   const int px = tile_x * GSR_TILE + (tid & (GSR_TILE - 1));
-  const int py = tile_y * GSR_TILE + (tid / GSR_TILE);
-  const bool inside = px < width && py < height;
-  const bool writable = px < width - 1 && py < height - 1;
+  const int py0 = tile_y * GSR_TILE + (tid / GSR_TILE) * PX;
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
-  const float fx = (float)px, fy = (float)py;
+  const float fx = (float)px;
 
-  float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
-  bool done = !writable;
-  uint32_t last = 0, seen = 0;
-  unsigned long long my_evals = 0;
-
-  for (uint32_t start = range.x; start < range.y; start += kBlendThreads) {
-    if (__syncthreads_count(!done) == 0) break;
-    const uint32_t idx = start + tid;
-    if (idx < range.y) {
-      const uint32_t g = __ldg(gids + idx);
-      float4 a = __ldg(rec + (size_t)g * 3), b = __ldg(rec + (size_t)g * 3 + 1);
-      const float c = __ldg((const float *)(rec + (size_t)g * 3 + 2));
-      if (blend_rank) {
-        const uint32_t r = __ldg(blend_rank + g);
-        if (r < first_rank || r >= last_rank) b.y = 0.0f;  // opacity 0 => alpha 0 => never kept
-      }
-      s_a[tid] = a;
-      s_b[tid] = b;
-      s_c[tid] = c;
-    }
-    __syncthreads();
-    const int count = min((uint32_t)kBlendThreads, range.y - start);
-    if (!done) {
-      for (int j = 0; j < count; ++j) {
-        const float4 a = s_a[j];
-        const float4 b = s_b[j];
-        ++seen;
-        if (COUNT) ++my_evals;
-        const float dx = fsub(a.x, fx), dy = fsub(a.y, fy);
-        const float power = fsub(fmul(-0.5f, fadd(fmul(a.z, fmul(dx, dx)), fmul(a.w, fmul(dy, dy)))),
-                                 fmul(fmul(b.x, dx), dy));
-        if (power > 0.0f) continue;
-        const float alpha = fminf(fmul(b.y, expf(power)), kMaxDensity);
-        if (!(alpha > kMinAlpha)) continue;
-        C0 = fadd(C0, fmul(fmul(alpha, b.z), T));
-        C1 = fadd(C1, fmul(fmul(alpha, b.w), T));
-        C2 = fadd(C2, fmul(fmul(alpha, s_c[j]), T));
-        T = fmul(T, fsub(1.0f, alpha));
-        last = seen;
-        if (T < kStopT) {
-          done = true;
-          break;
-        }
-      }
-    }
+  float fy[PX], T[PX], C0[PX], C1[PX], C2[PX];
+  uint32_t last[PX];
+  int live = 0;
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const bool writable = px < width - 1 && py0 + k < height - 1;  // Q8: last column / row are never written
+    fy[k] = writable ? (float)(py0 + k) : kParkedY;
+    live += writable;
+    T[k] = 1.0f;
+    C0[k] = C1[k] = C2[k] = 0.0f;
+    last[k] = 0;
   }
+  unsigned long long my_iters = 0, my_evals = 0;
+
+  const uint32_t total = range.y - range.x;
+  const int num_batches = (int)((total + kBatch - 1) / kBatch);
+  uint32_t gnext[PER];
+  auto load_ids = [&](int b) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const uint32_t idx = range.x + (uint32_t)b * kBatch + r * THREADS + tid;
+      gnext[r] = (b < num_batches && idx < range.y) ? __ldg(gids + idx) : 0xFFFFFFFFu;
+    }
+  };
+  auto issue = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      if (gnext[r] != 0xFFFFFFFFu) {
+        const float4 *src = rec + (size_t)gnext[r] * 3;
+        float *dst = &s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS];
+        cp_async16(dst, src);
+        cp_async16(dst + 4, src + 1);
+        cp_async16(dst + 8, src + 2);
+      }
+    }
+    cp_async_commit();
+  };
+  load_ids(0);
+  issue(0);
+  uint32_t gcur[PER];
+#pragma unroll
+  for (int r = 0; r < PER; ++r) gcur[r] = gnext[r];
+  load_ids(1);
+
+  for (int b = 0; b < num_batches; ++b) {
+    const int buf = b & 1;
+    uint32_t gmine[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) gmine[r] = gcur[r];
+    issue(buf ^ 1);  // batch b+1 (empty group when past the end)
+#pragma unroll
+    for (int r = 0; r < PER; ++r) gcur[r] = gnext[r];
+    load_ids(b + 2);
+    cp_async_wait<1>();  // batch b has landed for this thread's copies
+    if (RANKED) {        // progressive renders: records outside the rank window can never pass the test
+#pragma unroll
+      for (int r = 0; r < PER; ++r)
+        if (gmine[r] != 0xFFFFFFFFu) {
+          const uint32_t rk = __ldg(blend_rank + gmine[r]);
+          if (rk < first_rank || rk >= last_rank)
+            s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS + 5] = __int_as_float(0x7f800000);
+        }
+    }
+    if (__syncthreads_count(live > 0) == 0) break;
+    const int count = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
+    if (__any_sync(0xFFFFFFFFu, live > 0)) {  // warp-uniform: finished lanes idle along (their pixels are parked)
+      const float *base = s_rec[buf];
+#pragma unroll 2
+      for (int j = 0; j < count; ++j) {
+        const float4 q = *reinterpret_cast<const float4 *>(base + j * GSR_REC_FLOATS);      // mx my A C
+        const float2 w = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 4);  // B thr
+        if (COUNT) {
+          ++my_iters;
+          my_evals += live;
+        }
+        const float dx = fsub(q.x, fx);
+        const float adx2 = fmul(q.z, fmul(dx, dx));
+        const float bdx = fmul(w.x, dx);
+        float power[PX];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+          const float dy = fsub(q.y, fy[k]);
+          // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
+          power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
+          any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
+        }
+        if (any) {
+          const float2 orr = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 6);  // opacity r
+          const float2 gb = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 8);   // g b
+#pragma unroll
+          for (int k = 0; k < PX; ++k) {
+            if (power[k] >= w.y && power[k] <= 0.0f) {                                 // :291 (power <= 0)
+              const float alpha = fminf(fmul(orr.x, expf(power[k])), kMaxDensity);    // :285-288
+              if (alpha > kMinAlpha) {                                                // :291, strict, in f32
+                C0[k] = fadd(C0[k], fmul(fmul(alpha, orr.y), T[k]));                  // :295-297
+                C1[k] = fadd(C1[k], fmul(fmul(alpha, gb.x), T[k]));
+                C2[k] = fadd(C2[k], fmul(fmul(alpha, gb.y), T[k]));
+                T[k] = fmul(T[k], fsub(1.0f, alpha));                                 // :301-303
+                last[k] = (uint32_t)b * kBatch + j + 1;
+                if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
+                  fy[k] = kParkedY;
+                  --live;
+                }
+              }
+            }
+          }
+        }
+        // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
+        // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
+        // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
+        if ((j & 3) == 3 && __all_sync(0xFFFFFFFFu, live == 0)) break;
+      }
+    }
+    __syncthreads();  // everyone is done with s_rec[buf] before batch b+2 is gathered into it
+  }
+  cp_async_wait<0>();
+
   if (COUNT) {
-    // warp-granular count: a warp issues as many evaluation slots as its busiest lane consumed
-    unsigned long long mx = my_evals;
+    unsigned long long mx = my_iters;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
@@ -103,17 +189,21 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if ((tid & 31) == 0 && info) {
-      atomicAdd((unsigned long long *)&info->warp_evals, mx * 32ull);
-      atomicAdd((unsigned long long *)&info->pixel_evals, sum);
+      atomicAdd((unsigned long long *)&info->warp_evals, mx * 32ull * PX);  // evaluation slots the warp issued
+      atomicAdd((unsigned long long *)&info->pixel_evals, sum);             // of which: pixels still live
     }
   }
-  if (inside) {
-    const size_t p = (size_t)py * width + px;
-    image[p * 3 + 0] = C0;
-    image[p * 3 + 1] = C1;
-    image[p * 3 + 2] = C2;
-    if (final_T) final_T[p] = T;
-    if (n_contrib) n_contrib[p] = last;
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int py = py0 + k;
+    if (px < width && py < height) {
+      const size_t p = (size_t)py * width + px;
+      image[p * 3 + 0] = C0[k];
+      image[p * 3 + 1] = C1[k];
+      image[p * 3 + 2] = C2[k];
+      if (final_T) final_T[p] = T[k];
+      if (n_contrib) n_contrib[p] = last[k];
+    }
   }
 }
 
@@ -140,6 +230,17 @@ __global__ void blend_one_kernel(int x0, int y0, int x1, int y1, float mx, float
 
 using namespace gsr;
 
+// pixels per thread of the blend kernel: 4 unless GSR_BLEND_PX=2|4|8 is set (tuning knob, read once)
+static int blend_pixels_per_thread() {
+  static int px = 0;
+  if (px == 0) {
+    const char *e = getenv("GSR_BLEND_PX");
+    px = e ? atoi(e) : 4;
+    if (px != 2 && px != 4 && px != 8) px = 4;
+  }
+  return px;
+}
+
 extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const uint32_t *tile_ranges, int32_t width,
                              int32_t height, int32_t tile_row_begin, int32_t tile_row_end, const uint32_t *blend_rank,
                              uint32_t first_rank, uint32_t last_rank, float *image, float *final_T,
@@ -153,14 +254,20 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   if (tile_row_end <= tile_row_begin) return GSR_OK;
   if (first_rank == 0 && last_rank == 0xFFFFFFFFu) blend_rank = nullptr;
   dim3 grid(tg.tiles_x, tile_row_end - tile_row_begin);
-  if (info_dev)
-    blend_kernel<true><<<grid, kBlendThreads, 0, (cudaStream_t)stream>>>(
-        (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,
-        blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev);
-  else
-    blend_kernel<false><<<grid, kBlendThreads, 0, (cudaStream_t)stream>>>(
-        (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,
-        blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev);
+  const int px = blend_pixels_per_thread();
+#define GSR_BLEND_LAUNCH(PX, COUNT, RANKED)                                                                        \
+  blend_kernel<PX, COUNT, RANKED><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                                     \
+      (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
+      blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev)
+#define GSR_BLEND_PICK(PX)                                                          \
+  do {                                                                              \
+    if (blend_rank) {                                                               \
+      if (info_dev) GSR_BLEND_LAUNCH(PX, true, true); else GSR_BLEND_LAUNCH(PX, false, true);   \
+    } else {                                                                        \
+      if (info_dev) GSR_BLEND_LAUNCH(PX, true, false); else GSR_BLEND_LAUNCH(PX, false, false); \
+    }                                                                               \
+  } while (0)
+  if (px == 8) GSR_BLEND_PICK(8); else if (px == 2) GSR_BLEND_PICK(2); else GSR_BLEND_PICK(4);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

@@ -103,9 +103,13 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
   for (int c = 0; c < 3; ++c) rgb[c] = sh_channel(dx, dy, dz, degree, [&](int k) { return sh[c][k]; });
   const float opacity = sigmoid_ref(op_logit);
 
-  rec[i * 3 + 0] = make_float4(mx, my, ca, cc);
-  rec[i * 3 + 1] = make_float4(cb, opacity, rgb[0], rgb[1]);
-  rec[i * 3 + 2] = make_float4(rgb[2], camp[2], radius, 0.0f);
+  // Blend record (include/gsr_b200.h).  A = -a/2, C = -c/2, B = -b are exact rescalings of the reference's conic,
+  // so power = (A dx^2 + C dy^2) + (B dx) dy reproduces rasterize.py:280-283 bit for bit.  `thr` is a lower bound
+  // on the power at which alpha = o*exp(power) can exceed 1/255: below it the blend kernel skips the exp.
+  const float thr = opacity > 0.0f ? -logf(255.0f * opacity) - 1e-4f : __int_as_float(0x7f800000);
+  rec[i * 3 + 0] = make_float4(mx, my, fmul(-0.5f, ca), fmul(-0.5f, cc));
+  rec[i * 3 + 1] = make_float4(-cb, thr, opacity, rgb[0]);
+  rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], camp[2], radius);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -36,33 +36,54 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Lanes of the warp that hold the same 8-bit digit as the caller (8 ballots; cost independent of the number of
+// distinct digits, unlike __match_any_sync).  `live` == false lanes only match each other.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool live = true) {
+  uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
+  peers = live ? peers : ~peers;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, bit);
+    peers &= bit ? vote : ~vote;
+  }
+  return peers;
+}
+
 // ---- digit histograms of all passes, one read of the keys --------------------------------------------------
-__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n_host,
-                                                         const uint32_t *__restrict__ n_dev,
-                                                         uint32_t *__restrict__ hist, int begin_bit, int passes,
-                                                         uint32_t last_mask) {
-  __shared__ uint32_t s_hist[kMaxPasses][kRadix];
-  for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&s_hist[0][0])[k] = 0;
+// Shared-memory atomics cost ~2 cycles per lane whatever the address pattern, which made an atomic histogram the
+// slowest kernel of the sort.  Here each warp owns a private histogram and the lowest lane of every group of
+// equal digits adds the group's size with a plain read-modify-write (groups have distinct digits, so no two
+// lanes of the warp touch the same word).
+constexpr int kHistWarps = 8;
+__global__ void __launch_bounds__(kHistWarps * 32) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n_host,
+                                                                     const uint32_t *__restrict__ n_dev,
+                                                                     uint32_t *__restrict__ hist, int begin_bit,
+                                                                     int passes, uint32_t last_mask) {
+  extern __shared__ uint32_t s_hist[];  // [kHistWarps][passes][kRadix]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < kHistWarps * passes * kRadix; k += blockDim.x) s_hist[k] = 0;
   __syncthreads();
+  uint32_t *mine = s_hist + warp * passes * kRadix;
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
-  const int lane = threadIdx.x & 31;
-  // every warp runs the same trip count so that __match_any_sync sees full warps
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += stride) {
     const int64_t i = base + lane;
     const bool live = i < n;
-    const uint32_t key = live ? keys[i] : 0u;
+    const uint32_t key = live ? __ldg(keys + i) : 0u;
     for (int p = 0; p < passes; ++p) {
       uint32_t d = (key >> (begin_bit + 8 * p)) & 255u;
       if (p == passes - 1) d &= last_mask;
-      const uint32_t code = live ? d : 256u;  // dead lanes form their own group
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, code);
-      if (live && lane == __ffs(peers) - 1) atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+      const uint32_t peers = match_digit(d, live);
+      if (live && lane == __ffs(peers) - 1) mine[p * kRadix + d] += (uint32_t)__popc(peers);
     }
+    __syncwarp();
   }
   __syncthreads();
   for (int k = threadIdx.x; k < passes * kRadix; k += blockDim.x) {
-    const uint32_t v = (&s_hist[0][0])[k];
+    uint32_t v = 0;
+#pragma unroll
+    for (int w = 0; w < kHistWarps; ++w) v += s_hist[w * passes * kRadix + k];
     if (v) atomicAdd(&hist[k], v);
   }
 }
@@ -129,7 +150,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const uint32_t peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
     uint32_t before = 0;
     if (lane == leader) before = s_hist[warp][d];
@@ -223,9 +244,10 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
   const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
   GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
   {
-    int64_t want = ceil_div64(n, 256 * 8);
-    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-    radix_hist_kernel<<<blocks, 256, 0, stream>>>(keys_in, n, n_dev, s.hist, begin_bit, passes, last_mask);
+    int64_t want = ceil_div64(n, 256 * 16);
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+    const size_t smem = sizeof(uint32_t) * kHistWarps * passes * kRadix;
+    radix_hist_kernel<<<blocks, kHistWarps * 32, smem, stream>>>(keys_in, n, n_dev, s.hist, begin_bit, passes, last_mask);
     GSR_LAUNCH_CHECK();
   }
   const uint32_t *kin = keys_in, *vin = values_in;
