@@ -74,7 +74,7 @@ typedef struct gsr_frame_info {
 #define GSR_REC_FLOATS 12
 /*  [0] mean2d.x  [1] mean2d.y  [2] A = -a/2   [3] C = -c/2     (a, c, b) = sigmas, rasterize.py:404-411
  *  [4] B = -b    [5] thr       [6] opacity    [7] r            power = (A dx^2 + C dy^2) + (B dx) dy
- *  [8] g         [9] b(lue)    [10] depth z   [11] radius      thr = -ln(255 opacity) - 1e-4: alpha <= 1/255 below it */
+ *  [8] g         [9] b(lue)    [10] log2(o)   [11] radius      thr = -ln(255 opacity) - 1e-4: alpha <= 1/255 below it */
 
 const char *gsr_last_error(void);
 int gsr_abi_version(void);
@@ -115,10 +115,11 @@ int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t 
  *  rect[n,4]         u16 tile rect (x0,y0,x1,y1), clipped to the tile grid and to [row_begin,row_end)
  *  rec[n,12]         blend record (written for visible Gaussians only)
  * optional debug outputs (may be NULL): cov3d[n,9], cov2d[n,4] (after cull zeroing), tile_rect_raw[n,4] i32
- * (the reference's compute_covering_bbox result), radius[n]. */
+ * (the reference's compute_covering_bbox result), mean2d_all[n,2]; depth_hist[4*256] u32 receives the 8-bit digit
+ * histograms of depth_key (input of gsr_bin's one-sweep sort). */
 int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t tile_row_begin, int32_t tile_row_end,
                        uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, float *rec, float *cov3d,
-                       float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, void *stream);
+                       float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist, void *stream);
 
 /* spherical_harmonics.sh_to_rgb (spherical_harmonics.py:27-73): rgb[n,3] contiguous. */
 int gsr_sh_fwd(int64_t n, const float *xyz, int64_t xyz_sn, int64_t xyz_sc, const float *sh, int64_t sh_sn,
@@ -134,6 +135,8 @@ int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t 
 
 /* Binning: global stable depth sort (:424-425, ties by Gaussian index), duplication into (tile, Gaussian) pairs
  * in depth order, stable sort by tile, tile range extraction.  Equivalent to sorting 64-bit (tile|depth) keys.
+ *  depth_hist[4*256]  u32 digit histograms of depth_key as written by gsr_preprocess_fwd (in, may be NULL:
+ *                     they are then counted here)
  *  depth_order[n]     u32 Gaussian ids in ascending depth                 (out)
  *  blend_rank[n]      u32 rank of each visible Gaussian among the Gaussians the reference's loop would
  *                     blend, in blend order (out, may be NULL; feeds progressive renders)
@@ -141,10 +144,10 @@ int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t 
  *  tile_ranges[tiles,2] u32 [begin,end) into tile_gids                    (out)
  *  info_dev->n_dup / n_visible / status are filled (info_dev may be NULL). */
 int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
-int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *tiles_touched, const uint16_t *rect,
-            int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order, uint32_t *blend_rank,
-            uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
-            size_t workspace_bytes, void *stream);
+int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
+            const uint16_t *rect, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+            uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
+            void *workspace, size_t workspace_bytes, void *stream);
 
 /* Per-16x16-tile front-to-back alpha blend (:255-305, :436-446).  Pixels x >= W-1 or y >= H-1 are written
  * as zero (the reference never writes them).  When blend_rank is given, only Gaussians with

@@ -48,7 +48,9 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     rec = pre["rec"]
     # bit-exact against the reference itself (no exp involved)
     assert np.array_equal(_bits(pre["mean2d"]), _bits(g["mean2d"]))
-    assert np.array_equal(_bits(rec[:, 10]), _bits(g["depth"]))
+    key = pre["depth_key"].view(np.uint32)
+    depth_bits = np.where(key >> 31, key ^ np.uint32(0x80000000), ~key)  # invert the order-preserving map
+    assert np.array_equal(depth_bits.view(np.int32), _bits(g["depth"]))
     assert np.array_equal(_bits(rec[:, 7:10]), _bits(g["rgb"]))
     assert np.array_equal(_bits(rec[:, 6]), _bits(g["opacity"]))
     assert np.array_equal(pre["tile_rect"], g["tile_rect"])
@@ -61,7 +63,6 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     # exp-derived quantities agree with the reference to its own exp noise
     assert np.abs(pre["cov2d"] - g["cov2d"]).max() <= 2e-5 * np.abs(g["cov2d"]).max()
     # depth keys are an order-preserving image of the depths
-    key = pre["depth_key"].view(np.uint32)
     assert np.array_equal(np.argsort(key, kind="stable"), np.argsort(g["depth"], kind="stable"))
     # tiles touched: zero exactly for the Gaussians the reference's loop skips (rasterize.py:441)
     assert np.array_equal(pre["tiles_touched"] == 0, o["skip"] == 1)

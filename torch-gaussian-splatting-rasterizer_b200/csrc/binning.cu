@@ -7,7 +7,8 @@
 //   2. walk the Gaussians in depth order, warp-shuffle prefix scan of tiles-touched with a decoupled look-back
 //      across CTAs, and emit one (tile id, Gaussian id) pair per touched tile - pairs come out depth-ordered;
 //   3. stable sort of the pairs by tile id only (ceil(log2 tiles / 8) = 2 passes at 1080p);
-//   4. mark the [begin, end) range of every tile.
+//   4. the [begin, end) range of every tile comes from the per-tile list lengths counted during emission, whose
+//      marginals are also the digit histograms of the tile sort (no counting pass over the pairs).
 // Stability of both sorts makes ties fall back to the Gaussian index, i.e. the result is bit-identical to a
 // stable CPU sort of the 64-bit keys (tests/test_gpu_binning.py checks exactly that).
 // Replaces torch.sort at /root/reference/rasterize.py:424-425 and the implicit "for every Gaussian, for every
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles_touched,
                  const ushort4 *__restrict__ rect, int tiles_x, uint32_t capacity, unsigned long long *status,
                  BinCounters *ctr, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids,
-                 uint32_t *__restrict__ blend_rank, gsr_frame_info *info) {
+                 uint32_t *__restrict__ blend_rank, uint32_t *__restrict__ tile_count, gsr_frame_info *info) {
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_tile;
@@ -158,28 +159,67 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
     const uint32_t row = local / w, col = local - row * w;
     const uint32_t out = warp_out + e;
     if (out < capacity) {
-      tile_keys[out] = (r.y + row) * (uint32_t)tiles_x + r.x + col;
+      const uint32_t tile = (r.y + row) * (uint32_t)tiles_x + r.x + col;
+      tile_keys[out] = tile;
       tile_gids[out] = s_gid[warp][lo];
+      atomicAdd(tile_count + tile, 1u);  // fire-and-forget RED: list length of the tile
     }
   }
 }
 
-__global__ void tile_ranges_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_dev,
-                                   uint2 *__restrict__ ranges) {
-  const uint32_t n = *n_dev;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t t = keys[i];
-    if (i == 0 || keys[i - 1] != t) ranges[t].x = i;
-    if (i == n - 1 || keys[i + 1] != t) ranges[t].y = i + 1;
+// One CTA: exclusive scan of the per-tile list lengths -> [begin, end) of every tile, plus the digit histograms of
+// the tile-id sort (marginals of the same table), so the pairs are never read just to be counted.
+constexpr int kOffsThreads = 1024;
+__global__ void __launch_bounds__(kOffsThreads)
+tile_offsets_kernel(const uint32_t *__restrict__ tile_count, int num_tiles, uint2 *__restrict__ ranges,
+                    uint32_t *__restrict__ hist /*[passes][256]*/, int passes, uint32_t last_mask) {
+  __shared__ uint32_t s_warp[kOffsThreads / 32];
+  __shared__ uint32_t s_hist[2][256];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 512) (&s_hist[0][0])[tid] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < num_tiles; base += kOffsThreads) {
+    const int t = base + tid;
+    const uint32_t c = t < num_tiles ? tile_count[t] : 0u;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t pre = s_carry;
+    for (int w = 0; w < warp; ++w) pre += s_warp[w];
+    if (t < num_tiles) {
+      ranges[t] = make_uint2(pre + inc - c, pre + inc);
+      if (c) {
+        atomicAdd(&s_hist[0][t & 255], c);
+        if (passes > 1) atomicAdd(&s_hist[1][(t >> 8) & 255 & (passes == 2 ? last_mask : 255u)], c);
+      }
+    }
+    __syncthreads();
+    if (tid == kOffsThreads - 1) s_carry = pre + inc;
+    __syncthreads();
+  }
+  if (tid < 256) {
+    hist[tid] = passes == 1 ? 0u : s_hist[0][tid];
+    if (passes > 1) hist[256 + tid] = s_hist[1][tid];
+  }
+  if (passes == 1 && tid < 256) {  // single pass: the (masked) low digit is the whole key
+    // recompute with the mask applied: tiles < 256 here, so t & 255 & last_mask == t
+    hist[tid] = s_hist[0][tid];
   }
 }
 
 struct BinLayout {
-  size_t counters, scan_status, depth_sort, tile_sort, dkeys_tmp, dkeys_out, dvals_tmp, tkeys_a, tkeys_b, tkeys_c,
-      tgids_a, tgids_b, total;
+  size_t counters, scan_status, tile_count, tile_hist, depth_sort, tile_sort, dkeys_tmp, dkeys_out, dvals_tmp, tkeys_a,
+      tkeys_b, tkeys_c, tgids_a, tgids_b, total;
 };
 
-static BinLayout bin_layout(int64_t n, int64_t max_dup) {
+static BinLayout bin_layout(int64_t n, int64_t max_dup, int num_tiles) {
   BinLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -190,6 +230,8 @@ static BinLayout bin_layout(int64_t n, int64_t max_dup) {
   const int64_t n1 = n > 0 ? n : 1, d1 = max_dup > 0 ? max_dup : 1;
   L.counters = take(sizeof(BinCounters));
   L.scan_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kScanTile));
+  L.tile_count = take(sizeof(uint32_t) * (size_t)(num_tiles > 0 ? num_tiles : 1));
+  L.tile_hist = take(sizeof(uint32_t) * 4 * 256);
   L.depth_sort = take(sort_scratch_bytes(n1));
   L.tile_sort = take(sort_scratch_bytes(d1));
   L.dkeys_tmp = take(4 * (size_t)n1);
@@ -210,59 +252,66 @@ using namespace gsr;
 
 extern "C" int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes) {
   GSR_REQUIRE(bytes && n >= 0 && max_dup >= 0 && width > 0 && height > 0, "bad arguments");
-  *bytes = bin_layout(n, max_dup).total;
+  const TileGrid tg0 = make_grid(width, height);
+  *bytes = bin_layout(n, max_dup, tg0.tiles_x * tg0.tiles_y).total;
   return GSR_OK;
 }
 
-extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *tiles_touched, const uint16_t *rect,
-                       int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order, uint32_t *blend_rank,
-                       uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
-                       size_t workspace_bytes, void *stream_) {
+extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
+                       const uint16_t *rect, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+                       uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
+                       void *workspace, size_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GSR_REQUIRE(depth_key && tiles_touched && rect && depth_order && tile_gids && tile_ranges && workspace, "null pointer");
   GSR_REQUIRE(n >= 0 && n < (1ll << 30) && max_dup > 0 && max_dup < (1ll << 30), "n / max_dup out of range");
   GSR_REQUIRE(width > 0 && height > 0, "bad image size");
-  const BinLayout L = bin_layout(n, max_dup);
+  const TileGrid tg = make_grid(width, height);
+  const int num_tiles = tg.tiles_x * tg.tiles_y;
+  const BinLayout L = bin_layout(n, max_dup, num_tiles);
   if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("bin workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
     return GSR_ERR_WORKSPACE_TOO_SMALL;
   }
   char *ws = (char *)workspace;
-  const TileGrid tg = make_grid(width, height);
-  const int num_tiles = tg.tiles_x * tg.tiles_y;
   BinCounters *ctr = (BinCounters *)(ws + L.counters);
   unsigned long long *scan_status = (unsigned long long *)(ws + L.scan_status);
-  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.depth_sort - L.counters, stream));  // counters + scan status
-  GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
-  if (n == 0) return GSR_OK;
+  uint32_t *tile_count = (uint32_t *)(ws + L.tile_count), *tile_hist = (uint32_t *)(ws + L.tile_hist);
+  // counters + scan status + tile counts + tile digit histograms are contiguous: one memset
+  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.depth_sort - L.counters, stream));
+  if (n == 0) {
+    GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+    return GSR_OK;
+  }
 
-  // 1. global depth order (ties by Gaussian index)
+  // 1. global depth order (ties by Gaussian index); digit counts come from the preprocess kernel when available
   SortScratch s1, s2;
   int rc = sort_scratch_carve(ws + L.depth_sort, L.tile_sort - L.depth_sort, n, &s1);
   if (rc) return rc;
   rc = launch_sort_pairs(depth_key, nullptr, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
-                         (uint32_t *)(ws + L.dvals_tmp), n, nullptr, 0, 32, s1, stream, true);
+                         (uint32_t *)(ws + L.dvals_tmp), n, nullptr, 0, 32, s1, stream, true, depth_hist);
   if (rc) return rc;
 
-  // 2. prefix scan of tiles-touched in depth order + pair emission
+  // 2. prefix scan of tiles-touched in depth order + pair emission + per-tile list lengths
   uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
   scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, 0, stream>>>(
       n, depth_order, tiles_touched, (const ushort4 *)rect, tg.tiles_x, (uint32_t)max_dup, scan_status, ctr, tkeys_a,
-      tgids_a, blend_rank, info_dev);
+      tgids_a, blend_rank, tile_count, info_dev);
   GSR_LAUNCH_CHECK();
 
-  // 3. stable sort of the pairs by tile id
+  // 3. tile ranges and the digit histograms of the tile sort, both from the list lengths
   int tile_bits = 1;
   while ((1 << tile_bits) < num_tiles) ++tile_bits;
+  GSR_REQUIRE(tile_bits <= 16, "more than 65536 tiles are not supported by the two-pass tile sort");
+  const int passes = (tile_bits + 7) / 8;
+  const uint32_t last_mask = (1u << (tile_bits - 8 * (passes - 1))) - 1u;
+  tile_offsets_kernel<<<1, kOffsThreads, 0, stream>>>(tile_count, num_tiles, (uint2 *)tile_ranges, tile_hist, passes,
+                                                      last_mask);
+  GSR_LAUNCH_CHECK();
+
+  // 4. stable sort of the pairs by tile id
   rc = sort_scratch_carve(ws + L.tile_sort, L.dkeys_tmp - L.tile_sort, max_dup, &s2);
   if (rc) return rc;
-  uint32_t *tkeys_sorted = (uint32_t *)(ws + L.tkeys_c);
-  rc = launch_sort_pairs(tkeys_a, tgids_a, tkeys_sorted, tile_gids, (uint32_t *)(ws + L.tkeys_b),
-                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false);
-  if (rc) return rc;
-
-  // 4. [begin, end) of every tile
-  tile_ranges_kernel<<<148 * 8, 256, 0, stream>>>(tkeys_sorted, &ctr->n_dup, (uint2 *)tile_ranges);
-  GSR_LAUNCH_CHECK();
-  return GSR_OK;
+  rc = launch_sort_pairs(tkeys_a, tgids_a, (uint32_t *)(ws + L.tkeys_c), tile_gids, (uint32_t *)(ws + L.tkeys_b),
+                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, true, tile_hist);
+  return rc;
 }

@@ -37,6 +37,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -55,8 +60,14 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
 
   const int tid = threadIdx.x;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
-  const int px = tile_x * GSR_TILE + (tid & (GSR_TILE - 1));
-  const int py0 = tile_y * GSR_TILE + (tid / GSR_TILE) * PX;
+  // Lane -> pixel map: a warp owns 8 columns x 16 rows of the tile... a thread owns ONE column (dx is shared by its PX
+  // pixels) and the rows r, r+R, r+2R, ... with R = 16/PX, so that pixel slot k of the warp is the compact 8 x R block
+  // of rows kR..kR+R-1: a Gaussian reaches few slots, and a slot whose 32 pixels all fail the test costs nothing.
+  constexpr int R = GSR_TILE / PX;            // rows per slot block
+  constexpr int COLS = 32 / R;                // columns per warp
+  const int lane = tid & 31, warp = tid >> 5;
+  const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
+  const int py0 = tile_y * GSR_TILE + (lane / COLS);
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
   const float fx = (float)px;
 
@@ -65,8 +76,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   int live = 0;
 #pragma unroll
   for (int k = 0; k < PX; ++k) {
-    const bool writable = px < width - 1 && py0 + k < height - 1;  // Q8: last column / row are never written
-    fy[k] = writable ? (float)(py0 + k) : kParkedY;
+    const bool writable = px < width - 1 && py0 + k * R < height - 1;  // Q8: last column / row are never written
+    fy[k] = writable ? (float)(py0 + k * R) : kParkedY;
     live += writable;
     T[k] = 1.0f;
     C0[k] = C1[k] = C2[k] = 0.0f;
@@ -149,16 +160,21 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
         }
         if (any) {
           const float2 orr = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 6);  // opacity r
-          const float2 gb = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 8);   // g b
+          const float4 gbl = *reinterpret_cast<const float4 *>(base + j * GSR_REC_FLOATS + 8);  // g b log2(opacity) .
 #pragma unroll
           for (int k = 0; k < PX; ++k) {
-            if (power[k] >= w.y && power[k] <= 0.0f) {                                 // :291 (power <= 0)
-              const float alpha = fminf(fmul(orr.x, expf(power[k])), kMaxDensity);    // :285-288
-              if (alpha > kMinAlpha) {                                                // :291, strict, in f32
-                C0[k] = fadd(C0[k], fmul(fmul(alpha, orr.y), T[k]));                  // :295-297
-                C1[k] = fadd(C1[k], fmul(fmul(alpha, gb.x), T[k]));
-                C2[k] = fadd(C2[k], fmul(fmul(alpha, gb.y), T[k]));
-                T[k] = fmul(T[k], fsub(1.0f, alpha));                                 // :301-303
+            if (power[k] >= w.y) {
+              // alpha = min(o*exp(power), 0.99) (:285-288) as one FFMA + MUFU.EX2.  Its VALUE may differ from the
+              // reference's by a few 1e-7 (continuous, harmless); the DECISION alpha > 1/255 (:291) is discontinuous,
+              // so inside a +-1e-5 band around the threshold it is re-taken with the reference's own arithmetic.
+              float alpha = fminf(ex2_approx(fmaf(power[k], 1.4426950408889634f, gbl.z)), kMaxDensity);
+              if (fabsf(fmaf(alpha, 255.0f, -1.0f)) < 1e-5f) alpha = fminf(fmul(orr.x, expf(power[k])), kMaxDensity);
+              if (alpha > kMinAlpha && power[k] <= 0.0f) {
+                const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
+                C0[k] = fmaf(wgt, orr.y, C0[k]);
+                C1[k] = fmaf(wgt, gbl.x, C1[k]);
+                C2[k] = fmaf(wgt, gbl.y, C2[k]);
+                T[k] = fmaf(-alpha, T[k], T[k]);
                 last[k] = (uint32_t)b * kBatch + j + 1;
                 if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
                   fy[k] = kParkedY;
@@ -195,7 +211,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   }
 #pragma unroll
   for (int k = 0; k < PX; ++k) {
-    const int py = py0 + k;
+    const int py = py0 + k * R;
     if (px < width && py < height) {
       const size_t p = (size_t)py * width + px;
       image[p * 3 + 0] = C0[k];

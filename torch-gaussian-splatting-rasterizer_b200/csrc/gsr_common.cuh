@@ -77,6 +77,7 @@ size_t sort_scratch_bytes(int64_t n);
 int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *out);
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
-                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys);
+                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
+                      const uint32_t *ready_hist);
 
 }  // namespace gsr

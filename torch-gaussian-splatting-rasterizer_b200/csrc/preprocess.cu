@@ -14,13 +14,11 @@ __device__ __forceinline__ T ldg_stream(const T *p) {
   return __ldg(p);
 }
 
-__global__ void __launch_bounds__(kPreThreads)
-preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
-                  uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
-                  ushort4 *__restrict__ rect_out, float4 *__restrict__ rec, float *__restrict__ cov3d_out,
-                  float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out, float *__restrict__ mean2d_out) {
-  const int64_t i = (int64_t)blockIdx.x * kPreThreads + threadIdx.x;
-  if (i >= g.n) return;
+__device__ __forceinline__ uint32_t
+preprocess_one(const int64_t i, const gsr_gaussians &g, const gsr_camera &cam, int row_begin, int row_end,
+               uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
+               ushort4 *__restrict__ rect_out, float4 *__restrict__ rec, float *__restrict__ cov3d_out,
+               float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out, float *__restrict__ mean2d_out) {
 
   // ---- loads: everything this Gaussian needs is requested up front (59 independent 4-byte loads) ----
   float p[3], ls[3], rot[4];
@@ -72,7 +70,8 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
   uint32_t tiles = 0;
   if (!skip && x1 > x0 && y1 > y0) tiles = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
 
-  depth_key[i] = float_to_key(camp[2]);
+  const uint32_t key = float_to_key(camp[2]);
+  depth_key[i] = key;
   tiles_touched[i] = tiles;
   rect_out[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
 
@@ -93,7 +92,7 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
     mean2d_out[i * 2 + 1] = my;
   }
 
-  if (tiles == 0 && !cov3d_out) return;  // invisible: the blend never reads its record
+  if (tiles == 0 && !cov3d_out) return key;  // invisible: the blend never reads its record
 
   // ---- colour + opacity (spherical_harmonics.py:36-71, rasterize.py:358) ----
   float dx, dy, dz;
@@ -109,7 +108,41 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
   const float thr = opacity > 0.0f ? -logf(255.0f * opacity) - 1e-4f : __int_as_float(0x7f800000);
   rec[i * 3 + 0] = make_float4(mx, my, fmul(-0.5f, ca), fmul(-0.5f, cc));
   rec[i * 3 + 1] = make_float4(-cb, thr, opacity, rgb[0]);
-  rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], camp[2], radius);
+  rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], opacity > 0.0f ? log2f(opacity) : -1e30f, radius);
+  return key;
+}
+
+
+// Persistent grid-stride kernel.  Besides the per-Gaussian outputs it accumulates the four 8-bit digit histograms of
+// the depth keys (the one-sweep sort's global digit counts) in shared memory - the atomics ride on the otherwise
+// idle LSU pipe of this memory-bound kernel - and flushes them once per CTA.
+__global__ void __launch_bounds__(kPreThreads, 2)
+preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
+                  uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
+                  ushort4 *__restrict__ rect_out, float4 *__restrict__ rec, float *__restrict__ cov3d_out,
+                  float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out, float *__restrict__ mean2d_out,
+                  uint32_t *__restrict__ depth_hist) {
+  __shared__ uint32_t s_hist[4][256];
+  if (depth_hist) {
+    for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&s_hist[0][0])[k] = 0;
+    __syncthreads();
+  }
+  const int64_t stride = (int64_t)gridDim.x * kPreThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kPreThreads + threadIdx.x; i < g.n; i += stride) {
+    const uint32_t key = preprocess_one(i, g, cam, row_begin, row_end, depth_key, tiles_touched, rect_out, rec,
+                                        cov3d_out, cov2d_out, rect_raw_out, mean2d_out);
+    if (depth_hist) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
+    }
+  }
+  if (depth_hist) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += kPreThreads) {
+      const uint32_t v = (&s_hist[0][0])[k];
+      if (v) atomicAdd(depth_hist + k, v);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,7 +229,8 @@ using namespace gsr;
 
 extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t row_begin, int32_t row_end,
                                   uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, float *rec,
-                                  float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, void *stream) {
+                                  float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all,
+                                  uint32_t *depth_hist, void *stream) {
   GSR_REQUIRE(g && cam, "null gaussians/camera");
   GSR_REQUIRE(g->n >= 0 && g->n < (1ll << 31), "n out of range");
   GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
@@ -204,10 +238,14 @@ extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam,
               "image size out of range");
   GSR_REQUIRE(depth_key && tiles_touched && rect && rec, "null output");
   GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)rect & 7) == 0, "rec must be 16-byte and rect 8-byte aligned");
+  if (depth_hist) GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * 1024, (cudaStream_t)stream));
   if (g->n == 0) return GSR_OK;
-  preprocess_kernel<<<blocks_for(g->n, kPreThreads), kPreThreads, 0, (cudaStream_t)stream>>>(
+  unsigned blocks = blocks_for(g->n, kPreThreads);
+  const unsigned resident = 148 * 4;  // persistent: a few CTAs per SM, each loops over its share
+  if (blocks > resident) blocks = resident;
+  preprocess_kernel<<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(
       *g, *cam, row_begin, row_end, depth_key, tiles_touched, (ushort4 *)rect, (float4 *)rec, cov3d, cov2d,
-      tile_rect_raw, mean2d_all);
+      tile_rect_raw, mean2d_all, depth_hist);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

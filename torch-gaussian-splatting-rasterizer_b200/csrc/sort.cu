@@ -17,8 +17,8 @@
 
 namespace gsr {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per CTA
 constexpr int kRadix = 256;
 constexpr int kMaxPasses = 4;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kHistWarps * 32) radix_hist_kernel(const uint3
   }
 }
 
-// exclusive scan of one value per thread over a 256-thread CTA (two values at once)
+// exclusive scan of one (x, y) pair per thread over the first 256 threads of the CTA (called by ALL threads)
 __device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*[8]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint2 inc = v;
@@ -100,10 +100,10 @@ __device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*
       inc.y += ay;
     }
   }
-  if (lane == 31) s_warp[warp] = inc;
+  if (lane == 31 && warp < kRadix / 32) s_warp[warp] = inc;
   __syncthreads();
   uint2 pre = make_uint2(0, 0);
-  for (int w = 0; w < warp; ++w) {
+  for (int w = 0; w < warp && w < kRadix / 32; ++w) {
     pre.x += s_warp[w].x;
     pre.y += s_warp[w].y;
   }
@@ -117,17 +117,17 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
                 const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
                 uint32_t *ticket, int shift, uint32_t mask) {
-  __shared__ uint32_t s_hist[kSortThreads / 32][kRadix];  // per-warp digit counts, then exclusive over warps
+  __shared__ uint16_t s_hist[kSortThreads / 32][kRadix];  // per-warp digit counts (<= 256), then exclusive over warps (< 4096)
   __shared__ uint32_t s_excl[kRadix];                     // first tile-local slot of each digit
   __shared__ uint32_t s_gbase[kRadix];                    // global slot of a digit's first pair minus s_excl
   __shared__ uint32_t s_keys[kSortTile];
   __shared__ uint32_t s_vals[kSortTile];
-  __shared__ uint2 s_scan[kSortThreads / 32];
+  __shared__ uint2 s_scan[kRadix / 32];
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int k = tid; k < (kSortThreads / 32) * kRadix; k += kSortThreads) (&s_hist[0][0])[k] = 0;
+  for (int k = tid; k < (kSortThreads / 32) * kRadix / 2; k += kSortThreads) reinterpret_cast<uint32_t *>(&s_hist[0][0])[k] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
@@ -146,7 +146,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
 
   // ---- rank inside the warp, in (item, lane) order ----
-  uint16_t rank[kSortItems];
+  uint16_t rank[kSortItems];  // position among equal digits of this warp, in (item, lane) order
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
@@ -156,39 +156,53 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     if (lane == leader) before = s_hist[warp][d];
     before = __shfl_sync(0xFFFFFFFFu, before, leader);
     rank[i] = (uint16_t)(before + __popc(peers & ((1u << lane) - 1u)));
-    if (lane == leader) s_hist[warp][d] = before + __popc(peers);
+    if (lane == leader) s_hist[warp][d] = (uint16_t)(before + __popc(peers));
     __syncwarp();
   }
   __syncthreads();
 
-  // ---- thread d owns digit d: counts over warps -> exclusive, tile count, look-back ----
+  // ---- thread d (< 256) owns digit d: counts over warps -> exclusive, tile count, look-back ----
   uint32_t count = 0;
+  if (tid < kRadix) {
 #pragma unroll
-  for (int w = 0; w < kSortThreads / 32; ++w) {
-    const uint32_t c = s_hist[w][tid];
-    s_hist[w][tid] = count;
-    count += c;
-  }
-  const uint2 ex = block_exclusive_scan2(make_uint2(count, __ldg(hist + tid)), s_scan);
-  s_excl[tid] = ex.x;
-
-  uint32_t prefix = 0;
-  uint32_t *my_status = status + (size_t)tile * kRadix + tid;
-  if (tile == 0) {
-    st_volatile_u32(my_status, kFlagInclusive | count);
-  } else {
-    st_volatile_u32(my_status, kFlagAggregate | count);
-    const uint32_t *look = my_status - kRadix;
-    while (true) {
-      const uint32_t v = ld_volatile_u32(look);
-      if ((v >> 30) == 0) continue;  // predecessor has not published yet
-      prefix += v & kValueMask;
-      if (v & kFlagInclusive) break;
-      look -= kRadix;
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      const uint32_t c = s_hist[w][tid];
+      s_hist[w][tid] = (uint16_t)count;
+      count += c;
     }
-    st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
   }
-  s_gbase[tid] = ex.y + prefix - ex.x;
+  const uint2 ex = block_exclusive_scan2(make_uint2(count, tid < kRadix ? __ldg(hist + tid) : 0u), s_scan);
+  if (tid < kRadix) {
+    s_excl[tid] = ex.x;
+    uint32_t prefix = 0;
+    uint32_t *my_status = status + (size_t)tile * kRadix + tid;
+    if (tile == 0) {
+      st_volatile_u32(my_status, kFlagInclusive | count);
+    } else {
+      st_volatile_u32(my_status, kFlagAggregate | count);
+      // Decoupled look-back, kLookWindow predecessors per round trip: the loads of a window are independent, so
+      // a walk over w tiles costs ~w/kLookWindow L2 latencies instead of w.
+      constexpr int kLookWindow = 8;
+      int64_t prev = (int64_t)tile - 1;
+      bool open = true;
+      while (open) {
+        uint32_t v[kLookWindow];
+#pragma unroll
+        for (int i = 0; i < kLookWindow; ++i)
+          v[i] = (prev - i >= 0) ? ld_volatile_u32(status + (size_t)(prev - i) * kRadix + tid) : kFlagInclusive;
+#pragma unroll
+        for (int i = 0; i < kLookWindow; ++i) {
+          if (!open) break;
+          while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(status + (size_t)(prev - i) * kRadix + tid);
+          prefix += v[i] & kValueMask;
+          if (v[i] & kFlagInclusive) open = false;
+        }
+        prev -= kLookWindow;
+      }
+      st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
+    }
+    s_gbase[tid] = ex.y + prefix - ex.x;
+  }
   __syncthreads();
 
   // ---- scatter to the tile-local sorted position, then write runs of equal digits coalesced ----
@@ -231,7 +245,8 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
 
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
-                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys) {
+                      int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
+                      const uint32_t *ready_hist) {
   GSR_REQUIRE(n >= 0 && n < (1ll << 30), "sort size out of range (must be < 2^30)");
   GSR_REQUIRE(begin_bit >= 0 && end_bit <= 32 && end_bit > begin_bit, "bad bit range");
   GSR_REQUIRE(keys_in && keys_out && values_out && keys_tmp && values_tmp, "null sort buffer");
@@ -243,7 +258,8 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
   const int64_t tiles = ceil_div64(n, kSortTile);
   const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
   GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
-  {
+  const uint32_t *hist = ready_hist ? ready_hist : s.hist;  // digit counts may come from the producer of the keys
+  if (!ready_hist) {
     int64_t want = ceil_div64(n, 256 * 16);
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
     const size_t smem = sizeof(uint32_t) * kHistWarps * passes * kRadix;
@@ -257,7 +273,7 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     uint32_t *vout = to_out ? values_out : values_tmp;
     if (p == passes - 1 && skip_final_keys) kout = nullptr;  // caller only wants the permutation
     const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
-    onesweep_kernel<<<(unsigned)tiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, s.hist + p * kRadix,
+    onesweep_kernel<<<(unsigned)tiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, hist + p * kRadix,
                                                                   s.status + p * s.status_stride, s.tickets + p,
                                                                   begin_bit + 8 * p, mask);
     GSR_LAUNCH_CHECK();
@@ -285,5 +301,5 @@ extern "C" int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in
   int rc = sort_scratch_carve(workspace, workspace_bytes, n, &s);
   if (rc) return rc;
   return launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, n_dev, begin_bit,
-                           end_bit, s, (cudaStream_t)stream, false);
+                           end_bit, s, (cudaStream_t)stream, false, nullptr);
 }
