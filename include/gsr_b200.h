@@ -111,15 +111,19 @@ int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t 
 /* Fused per-Gaussian preprocess: :97-120 (Sigma), :358 (sigmoid), :371-420 (projection, cull, EWA, radius,
  * tile rect, conic, skip rule :441) and spherical_harmonics.py:27-73.
  *  depth_key[n]      u32, order-preserving bits of z_cam (:424)
- *  tiles_touched[n]  u32, 0 for culled / skipped / off-screen Gaussians
+ *  tiles_touched[n]  u32: bit 31 = the reference's loop would blend this Gaussian (not culled / skipped / off
+ *                    screen, :441); bits 0..30 = number of tiles of its rect in which at least one pixel can pass
+ *                    alpha > 1/255 (exact tile culling, see gsr_math.cuh) - the image is unchanged by the culling
  *  rect[n,4]         u16 tile rect (x0,y0,x1,y1), clipped to the tile grid and to [row_begin,row_end)
+ *  tile_mask[n,2]    u32 x2: keep mask of the rect's tiles, row-major, for rects of <= 64 tiles (larger: all kept)
  *  rec[n,12]         blend record (written for visible Gaussians only)
  * optional debug outputs (may be NULL): cov3d[n,9], cov2d[n,4] (after cull zeroing), tile_rect_raw[n,4] i32
  * (the reference's compute_covering_bbox result), mean2d_all[n,2]; depth_hist[4*256] u32 receives the 8-bit digit
  * histograms of depth_key (input of gsr_bin's one-sweep sort). */
 int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t tile_row_begin, int32_t tile_row_end,
-                       uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, float *rec, float *cov3d,
-                       float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist, void *stream);
+                       uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, uint32_t *tile_mask, float *rec,
+                       float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist,
+                       void *stream);
 
 /* spherical_harmonics.sh_to_rgb (spherical_harmonics.py:27-73): rgb[n,3] contiguous. */
 int gsr_sh_fwd(int64_t n, const float *xyz, int64_t xyz_sn, int64_t xyz_sc, const float *sh, int64_t sh_sn,
@@ -145,7 +149,7 @@ int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t 
  *  info_dev->n_dup / n_visible / status are filled (info_dev may be NULL). */
 int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
 int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
-            const uint16_t *rect, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+            const uint16_t *rect, const uint32_t *tile_mask, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
             uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
             void *workspace, size_t workspace_bytes, void *stream);
 

@@ -137,3 +137,14 @@ def tile_lists(pre: Dict[str, np.ndarray], width: int, height: int):
     starts = np.searchsorted(tile, np.arange(tiles_x * tiles_y), side="left")
     ends = np.searchsorted(tile, np.arange(tiles_x * tiles_y), side="right")
     return tile, gid, np.stack([starts, ends], axis=1)
+
+
+def pair_hits(pre: Dict[str, np.ndarray], gids: np.ndarray, tiles: np.ndarray, width: int, height: int) -> np.ndarray:
+    """For each (Gaussian, tile) pair: does any pixel of the tile pass the reference's keep test?"""
+    c = np.ascontiguousarray
+    gids, tiles = c(gids, dtype=np.int64), c(tiles, dtype=np.int64)
+    hits = np.zeros(gids.shape[0], np.uint8)
+    mean2d, conic, op = c(pre["mean2d"], dtype=np.float32), c(pre["conic"], dtype=np.float32), c(pre["opacity"], dtype=np.float32)
+    lib().gsr_oracle_pair_hits(ctypes.c_int64(gids.shape[0]), _p(gids), _p(tiles), ctypes.c_int((width + 15) // 16),
+                               ctypes.c_int(width), ctypes.c_int(height), _p(mean2d), _p(conic), _p(op), _p(hits))
+    return hits

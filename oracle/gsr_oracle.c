@@ -346,6 +346,33 @@ int64_t gsr_oracle_blend(int64_t n_order, const int64_t *order, const uint8_t *s
   return blended;
 }
 
+/*
+ * For (Gaussian, tile) pairs: does ANY pixel of the 16x16 tile pass the reference's keep test (rasterize.py:285-291)
+ * for that Gaussian?  Used to check that the pairs the CUDA binning drops ("exact tile culling") could not have
+ * changed the image.  Same arithmetic as blend_one; pixels x >= W-1 or y >= H-1 are never written (Q8).
+ */
+void gsr_oracle_pair_hits(int64_t n_pairs, const int64_t *gids, const int64_t *tiles, int tiles_x, int W, int H,
+                          const float *mean2d, const float *conic, const float *opacity, uint8_t *hits) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    const int64_t g = gids[p];
+    const int tx = (int)(tiles[p] % tiles_x), ty = (int)(tiles[p] / tiles_x);
+    const float a = conic[3 * g], c = conic[3 * g + 1], bxy = conic[3 * g + 2];
+    const float mx = mean2d[2 * g], my = mean2d[2 * g + 1], o = opacity[g];
+    uint8_t hit = 0;
+    for (int x = tx * BLOCK; x < tx * BLOCK + BLOCK && x < W - 1 && !hit; ++x) {
+      float dx = mx - (float)x;
+      for (int y = ty * BLOCK; y < ty * BLOCK + BLOCK && y < H - 1; ++y) {
+        float dy = my - (float)y;
+        float power = -0.5f * (a * (dx * dx) + c * (dy * dy)) - (bxy * dx) * dy;
+        float alpha = fminf(o * expf(power), MAX_DENSITY);
+        if (alpha > MIN_ALPHA && power <= 0.0f) { hit = 1; break; }
+      }
+    }
+    hits[p] = hit;
+  }
+}
+
 /* Sum over Gaussians of bbox pixels = number of Gaussian-pixel evaluations the reference performs. */
 int64_t gsr_oracle_count_evals(int64_t n, const uint8_t *skip, const int32_t *bb) {
   int64_t tot = 0;

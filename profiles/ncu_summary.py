@@ -10,6 +10,21 @@ def launches(path):
     for k, v in agg.items():
         print(f"{k:50s} n={len(v):3d} mean={sum(v)/len(v):9.1f} us  share={100*sum(v)/tot:5.1f}%")
 
+TERSE = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+         "launch__registers_per_thread", "dram__bytes_read.sum", "dram__bytes_write.sum"]
+STALLS = "smsp__average_warps_issue_stalled_"
+
+def terse(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        st = sorted(((float(v), k[len(STALLS):].split("_per_")[0]) for k, v in d.items() if k.startswith(STALLS) and k.endswith("ratio") and "selected" not in k), reverse=True)[:4]
+        print(d["Kernel Name"].split("(")[0][:32], "|", " ".join(f"{k.split('.')[0].split('__')[-1]}={d[k]}" for k in TERSE if k in d),
+              "| stalls:", " ".join(f"{n}={v:.1f}" for v, n in st))
+
 KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -31,4 +46,4 @@ def raw(path):
                 print(f"  {h:86s} {v:>16s} {u}")
 
 if __name__ == "__main__":
-    (launches if sys.argv[1] == "launches" else raw)(sys.argv[2])
+    {"launches": launches, "raw": raw, "terse": terse}[sys.argv[1]](sys.argv[2])

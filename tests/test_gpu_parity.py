@@ -64,8 +64,12 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     assert np.abs(pre["cov2d"] - g["cov2d"]).max() <= 2e-5 * np.abs(g["cov2d"]).max()
     # depth keys are an order-preserving image of the depths
     assert np.array_equal(np.argsort(key, kind="stable"), np.argsort(g["depth"], kind="stable"))
-    # tiles touched: zero exactly for the Gaussians the reference's loop skips (rasterize.py:441)
-    assert np.array_equal(pre["tiles_touched"] == 0, o["skip"] == 1)
+    # bit 31 of tiles_touched: set exactly for the Gaussians the reference's loop blends (rasterize.py:441);
+    # low bits: tiles kept by the exact culling, never more than the rect holds
+    tt = pre["tiles_touched"].view(np.uint32)
+    assert np.array_equal((tt >> 31) == 1, o["skip"] == 0)
+    r = pre["rect"].astype(np.int64)
+    assert ((tt & 0x7FFFFFFF) <= (r[:, 2] - r[:, 0]) * (r[:, 3] - r[:, 1]))[o["skip"] == 0].all()
 
 
 @pytest.mark.parametrize("n,bits", [(1, 32), (255, 32), (4096, 32), (4097, 32), (100_003, 32), (1_000_000, 32),
@@ -92,17 +96,36 @@ def test_radix_sort_is_the_stable_sort(n, bits, R):
 
 @pytest.mark.parametrize("name", NAMES)
 def test_binning_equals_stable_sort_of_tile_depth_keys(name, golden, R):
+    """Tile lists = the stable sort by (tile, depth bits, Gaussian index) of the reference's (Gaussian, tile) pairs,
+    minus pairs in which no pixel can pass the reference's keep test (exact tile culling)."""
     cloud, intr, view, cam = _case(name)
     o = c_oracle.render(cloud, cam)
-    tile, gid, ranges = c_oracle.tile_lists(o, cam.width, cam.height)
+    tile, gid, ranges = c_oracle.tile_lists(o, cam.width, cam.height)  # every pair of the reference, sorted
     model = R.GaussianModel.from_cloud(cloud)
     pre = R.preprocess(model, cam)
     binned = R.bin_tiles(pre, cam.width, cam.height, max_dup=max(1024, 2 * tile.shape[0]))
     info = binned["info"].cpu().numpy().view(np.uint32)
-    assert info[0] == 0 and info[2] == tile.shape[0] and info[1] == int((o["skip"] == 0).sum())
+    n_dup = int(info[2])
+    assert info[0] == 0 and info[1] == int((o["skip"] == 0).sum()) and 0 < n_dup <= tile.shape[0]
     assert np.array_equal(binned["order"].cpu().numpy(), golden(name)["order"])  # the reference's (stable) depth order
-    assert np.array_equal(binned["tile_gids"].cpu().numpy()[: tile.shape[0]], gid)
-    assert np.array_equal(binned["tile_ranges"].cpu().numpy(), ranges)
+    got_gid = binned["tile_gids"].cpu().numpy()[:n_dup].astype(np.int64)
+    got_rng = binned["tile_ranges"].cpu().numpy().astype(np.int64)
+    assert got_rng[-1, 1] == n_dup and (got_rng[1:, 0] == got_rng[:-1, 1]).all() and got_rng[0, 0] == 0
+    got_tile = np.repeat(np.arange(got_rng.shape[0]), got_rng[:, 1] - got_rng[:, 0])
+    # the kept pairs are a subsequence of the reference's sorted pairs (same order => same per-pixel blend order)
+    tiles_n = got_rng.shape[0]
+    ref_code, got_code = tile * cloud.n + gid, got_tile * cloud.n + got_gid
+    pos = np.searchsorted(ref_code, got_code)  # ref_code is strictly increasing in (tile, then list position)?
+    lookup = {int(c): i for i, c in enumerate(ref_code)}
+    idx = np.array([lookup[int(c)] for c in got_code])
+    assert (np.diff(idx) > 0).all(), "kept pairs are not in the reference's order"
+    # every dropped pair is one the reference would have evaluated without blending a single pixel
+    dropped = np.ones(tile.shape[0], bool); dropped[idx] = False
+    hits = c_oracle.pair_hits(o, gid[dropped], tile[dropped], cam.width, cam.height)
+    assert not hits.any(), f"{int(hits.sum())} dropped pairs would have contributed"
+    # ... and the culling is not vacuous on these scenes
+    kept_hits = c_oracle.pair_hits(o, gid[idx], tile[idx], cam.width, cam.height)
+    assert kept_hits.mean() > 0.7
     # blend rank = position among the Gaussians the reference's loop blends
     blended = o["order"][o["skip"][o["order"]] == 0]
     assert np.array_equal(binned["blend_rank"].cpu().numpy()[blended], np.arange(blended.shape[0]))

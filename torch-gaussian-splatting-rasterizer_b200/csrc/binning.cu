@@ -16,7 +16,7 @@
 //
 // The number of pairs never travels to the host: it is left in device memory (clamped to the caller's capacity,
 // overflow flagged in gsr_frame_info.status) and every later kernel reads it from there.
-#include "gsr_common.cuh"
+#include "gsr_math.cuh"
 
 namespace gsr {
 
@@ -50,7 +50,8 @@ __device__ __forceinline__ unsigned long long pack_scan(uint32_t tiles, uint32_t
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *__restrict__ tiles_touched,
-                 const ushort4 *__restrict__ rect, int tiles_x, uint32_t capacity, unsigned long long *status,
+                 const ushort4 *__restrict__ rect, const uint2 *__restrict__ tile_mask, int tiles_x, uint32_t capacity,
+                 unsigned long long *status,
                  BinCounters *ctr, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids,
                  uint32_t *__restrict__ blend_rank, uint32_t *__restrict__ tile_count, gsr_frame_info *info) {
   __shared__ unsigned long long s_warp[kScanThreads / 32];
@@ -62,18 +63,21 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
   const uint32_t tile = s_tile;
   const int64_t first = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
 
-  uint32_t gid[kScanItems], cnt[kScanItems];
+  uint32_t gid[kScanItems], cnt[kScanItems], vis[kScanItems];
   unsigned long long mine = 0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     const int64_t pos = first + j;
     gid[j] = 0;
     cnt[j] = 0;
+    vis[j] = 0;
     if (pos < n) {
       gid[j] = __ldg(order + pos);
-      cnt[j] = __ldg(tiles_touched + gid[j]);
+      const uint32_t t = __ldg(tiles_touched + gid[j]);
+      cnt[j] = t & 0x7FFFFFFFu;  // tiles kept after culling
+      vis[j] = t >> 31;          // the reference's loop would blend it (rank numbering of progressive renders)
     }
-    mine += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
+    mine += pack_scan(cnt[j], vis[j]);
   }
   // warp-shuffle inclusive scan, then across warps
   unsigned long long inc = mine;
@@ -126,6 +130,7 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
   __shared__ uint32_t s_off[kScanThreads / 32][32 * kScanItems + 1];
   __shared__ uint32_t s_gid[kScanThreads / 32][32 * kScanItems];
   __shared__ ushort4 s_rect[kScanThreads / 32][32 * kScanItems];
+  __shared__ uint2 s_mask[kScanThreads / 32][32 * kScanItems];
   const unsigned long long thread_excl = s_base + pre + inc - mine;  // exclusive prefix of this thread's first item
   const unsigned long long warp_excl = __shfl_sync(0xFFFFFFFFu, thread_excl, 0);
   const uint32_t warp_out = (uint32_t)(warp_excl & 0x7FFFFFFFull);
@@ -138,9 +143,10 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
       s_gid[warp][slot] = gid[j];
       if (cnt[j]) {
         s_rect[warp][slot] = __ldg(rect + gid[j]);
-        if (blend_rank) blend_rank[gid[j]] = (uint32_t)(run >> 31);  // rank among the Gaussians the reference would blend
+        s_mask[warp][slot] = __ldg(tile_mask + gid[j]);
       }
-      run += pack_scan(cnt[j], cnt[j] ? 1u : 0u);
+      if (vis[j] && blend_rank) blend_rank[gid[j]] = (uint32_t)(run >> 31);  // rank among the Gaussians the reference blends
+      run += pack_scan(cnt[j], vis[j]);
     }
     if (lane == 31) s_off[warp][32 * kScanItems] = (uint32_t)(run & 0x7FFFFFFFull) - warp_out;
   }
@@ -154,8 +160,12 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
       if (s_off[warp][mid] <= e) lo = mid; else hi = mid - 1;
     }
     const ushort4 r = s_rect[warp][lo];
-    const uint32_t local = e - s_off[warp][lo];
+    uint32_t local = e - s_off[warp][lo];
     const uint32_t w = (uint32_t)(r.z - r.x);
+    if (w * (uint32_t)(r.w - r.y) <= (uint32_t)kCullMaxTiles) {  // local-th KEPT tile of the keep mask (all ones if untested)
+      const uint2 km = s_mask[warp][lo];
+      local = nth_set_bit(km.x, km.y, local);
+    }
     const uint32_t row = local / w, col = local - row * w;
     const uint32_t out = warp_out + e;
     if (out < capacity) {
@@ -258,11 +268,13 @@ extern "C" int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height,
 }
 
 extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
-                       const uint16_t *rect, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+                       const uint16_t *rect, const uint32_t *tile_mask, int32_t width, int32_t height, int64_t max_dup,
+                       uint32_t *depth_order,
                        uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
                        void *workspace, size_t workspace_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  GSR_REQUIRE(depth_key && tiles_touched && rect && depth_order && tile_gids && tile_ranges && workspace, "null pointer");
+  GSR_REQUIRE(depth_key && tiles_touched && rect && tile_mask && depth_order && tile_gids && tile_ranges && workspace,
+              "null pointer");
   GSR_REQUIRE(n >= 0 && n < (1ll << 30) && max_dup > 0 && max_dup < (1ll << 30), "n / max_dup out of range");
   GSR_REQUIRE(width > 0 && height > 0, "bad image size");
   const TileGrid tg = make_grid(width, height);
@@ -294,7 +306,8 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   // 2. prefix scan of tiles-touched in depth order + pair emission + per-tile list lengths
   uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
   scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, 0, stream>>>(
-      n, depth_order, tiles_touched, (const ushort4 *)rect, tg.tiles_x, (uint32_t)max_dup, scan_status, ctr, tkeys_a,
+      n, depth_order, tiles_touched, (const ushort4 *)rect, (const uint2 *)tile_mask, tg.tiles_x, (uint32_t)max_dup,
+      scan_status, ctr, tkeys_a,
       tgids_a, blend_rank, tile_count, info_dev);
   GSR_LAUNCH_CHECK();
 

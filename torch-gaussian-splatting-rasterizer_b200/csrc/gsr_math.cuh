@@ -195,6 +195,56 @@ __device__ __forceinline__ float sh_channel(float x, float y, float z, int degre
   return clampf(col, 0.0f, 1.0f);
 }
 
+// ---- exact tile culling ------------------------------------------------------------------------------------
+// A (Gaussian, tile) pair can only change the image if some pixel of the tile passes the reference's keep test
+// alpha = o*exp(power) > 1/255 (rasterize.py:291), i.e. power >= thr.  power is a concave quadratic of the pixel
+// position, so its maximum over the tile's pixel box is 0 when the mean lies inside and otherwise sits on one of
+// the four edges, where it is a clamped 1-D parabola.  Pairs whose maximum stays below thr (minus a rounding
+// margin) are dropped from the tile lists: the image is unchanged, binning and blending get ~35 % less work.
+// Used by BOTH the count (preprocess) and the emission (binning) so they always agree.
+struct CullGaussian {
+  float mx, my, A, C, B, kv, ku, limit;  // kv = -B/(2C), ku = -B/(2A); limit = thr - margin(thr)
+};
+__device__ __forceinline__ CullGaussian make_cull(float mx, float my, float A, float C, float B, float thr) {
+  CullGaussian g;
+  g.mx = mx; g.my = my; g.A = A; g.C = C; g.B = B;
+  g.kv = -B / (2.0f * C);
+  g.ku = -B / (2.0f * A);
+  g.limit = thr - 1e-4f * (1.0f + fabsf(thr));
+  return g;
+}
+__device__ __forceinline__ float parabola_max(float q2, float q1, float q0, float t_opt, float lo, float hi) {
+  const float t = fminf(fmaxf(t_opt, lo), hi);
+  return fmaf(fmaf(q2, t, q1), t, q0);
+}
+// true when no pixel with x in [px0,px1], y in [py0,py1] can pass the keep test
+__device__ __forceinline__ bool tile_is_empty(const CullGaussian &g, float px0, float py0, float px1, float py1) {
+  const float u0 = px0 - g.mx, u1 = px1 - g.mx, v0 = py0 - g.my, v1 = py1 - g.my;
+  if (u0 <= 0.0f && u1 >= 0.0f && v0 <= 0.0f && v1 >= 0.0f) return false;  // mean inside: power reaches 0
+  // edges u = u0 / u1: f(v) = C v^2 + (B u) v + A u^2 ; edges v = v0 / v1: f(u) = A u^2 + (B v) u + C v^2
+  float best = parabola_max(g.C, g.B * u0, g.A * u0 * u0, g.kv * u0, v0, v1);
+  best = fmaxf(best, parabola_max(g.C, g.B * u1, g.A * u1 * u1, g.kv * u1, v0, v1));
+  best = fmaxf(best, parabola_max(g.A, g.B * v0, g.C * v0 * v0, g.ku * v0, u0, u1));
+  best = fmaxf(best, parabola_max(g.A, g.B * v1, g.C * v1 * v1, g.ku * v1, u0, u1));
+  // rounding margin proportional to the largest term that can cancel inside `power` on this box
+  const float U = fmaxf(fabsf(u0), fabsf(u1)), V = fmaxf(fabsf(v0), fabsf(v1));
+  const float mag = fabsf(g.A) * U * U + fabsf(g.C) * V * V + fabsf(g.B) * U * V;
+  return best < g.limit - 1.52587890625e-05f * mag;  // any NaN compares false -> keep
+}
+constexpr int kCullMaxTiles = 64;  // rects up to 64 tiles carry a 64-bit keep mask; larger ones are not culled
+
+// position of the n-th (0-based) set bit of a 64-bit mask (lo, hi); n < popc(mask)
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t lo, uint32_t hi, uint32_t n) {
+  uint32_t c = __popc(lo), m = lo, base = 0;
+  if (n >= c) { n -= c; m = hi; base = 32; }
+  c = __popc(m & 0xFFFFu); if (n >= c) { n -= c; base += 16; m >>= 16; }
+  c = __popc(m & 0xFFu);   if (n >= c) { n -= c; base += 8;  m >>= 8; }
+  c = __popc(m & 0xFu);    if (n >= c) { n -= c; base += 4;  m >>= 4; }
+  c = __popc(m & 0x3u);    if (n >= c) { n -= c; base += 2;  m >>= 2; }
+  if (n >= (m & 1u)) base += 1;
+  return base;
+}
+
 __device__ __forceinline__ void view_direction(const float p[3], const float cc[3], float &x, float &y, float &z) {
   float dx = fsub(p[0], cc[0]), dy = fsub(p[1], cc[1]), dz = fsub(p[2], cc[2]);
   float nrm = fsqrt(fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));

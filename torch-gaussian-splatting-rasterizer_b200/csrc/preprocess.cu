@@ -14,126 +14,203 @@ __device__ __forceinline__ T ldg_stream(const T *p) {
   return __ldg(p);
 }
 
-__device__ __forceinline__ uint32_t
-preprocess_one(const int64_t i, const gsr_gaussians &g, const gsr_camera &cam, int row_begin, int row_end,
-               uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
-               ushort4 *__restrict__ rect_out, float4 *__restrict__ rec, float *__restrict__ cov3d_out,
-               float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out, float *__restrict__ mean2d_out) {
-
-  // ---- loads: everything this Gaussian needs is requested up front (59 independent 4-byte loads) ----
-  float p[3], ls[3], rot[4];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) p[c] = __ldg(g.xyz + i * g.xyz_sn + c * g.xyz_sc);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) ls[c] = __ldg(g.log_scales + i * g.scale_sn + c * g.scale_sc);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) rot[c] = __ldg(g.rots + i * g.rot_sn + c * g.rot_sc);
-  const float op_logit = __ldg(g.opacity_logit + i * g.opacity_sn);
-  const int degree = cam.sh_degree;
-  const int ncoef = (degree + 1) * (degree + 1);
-  float sh[3][16];
-  const float *shp = g.sh + i * g.sh_sn;
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) sh[c][k] = (k < ncoef) ? __ldg(shp + k * g.sh_sk + c * g.sh_sc) : 0.0f;
-
-  // ---- geometry: rasterize.py:371-420 ----
-  float camp[3], clip[4];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) camp[c] = row_affine(cam.w2c_t, c, p[0], p[1], p[2]);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) clip[c] = row_affine(cam.full_t, c, p[0], p[1], p[2]);
-  const bool culled = camp[2] < 0.2f;  // :377
-  if (culled) clip[0] = clip[1] = clip[3] = 0.0f;
-  const float pw = frcp(fadd(clip[3], 0.0000001f));  // :381
-  const float mx = fdiv(fsub(fmul(fadd(fmul(clip[0], pw), 1.0f), (float)cam.width), 1.0f), 2.0f);   // :391
-  const float my = fdiv(fsub(fmul(fadd(fmul(clip[1], pw), 1.0f), (float)cam.height), 1.0f), 2.0f);
-
-  float S[9], c2[4];
-  covariance3d(ls, rot, S);
-  covariance2d(S, camp, cam, c2);
-  if (culled) c2[0] = c2[1] = c2[2] = c2[3] = 0.0f;  // :388
-  float radius;
-  int rr[4];
-  covering_rect(mx, my, c2, cam.width, cam.height, radius, rr);
-  float ca, cc, cb;
-  conic_from_cov(c2, ca, cc, cb);
-
-  // tile rect clipped to the writable tile grid and to this rank's band of tile rows
-  const TileGrid tg = make_grid(cam.width, cam.height);
-  int x0 = min(rr[0], tg.tiles_x_eff), x1 = min(rr[2], tg.tiles_x_eff);
-  int y0 = min(rr[1], tg.tiles_y_eff), y1 = min(rr[3], tg.tiles_y_eff);
-  y0 = max(y0, row_begin);
-  y1 = min(y1, row_end);
-  const bool skip = (ca == 0.0f) | (cc == 0.0f) | (cb == 0.0f);  // :441 ("any conic component is zero")
-  uint32_t tiles = 0;
-  if (!skip && x1 > x0 && y1 > y0) tiles = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
-
-  const uint32_t key = float_to_key(camp[2]);
-  depth_key[i] = key;
-  tiles_touched[i] = tiles;
-  rect_out[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-
-  if (cov3d_out) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) cov3d_out[i * 9 + k] = S[k];
-  }
-  if (cov2d_out) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cov2d_out[i * 4 + k] = c2[k];
-  }
-  if (rect_raw_out) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) rect_raw_out[i * 4 + k] = rr[k];
-  }
-  if (mean2d_out) {
-    mean2d_out[i * 2] = mx;
-    mean2d_out[i * 2 + 1] = my;
-  }
-
-  if (tiles == 0 && !cov3d_out) return key;  // invisible: the blend never reads its record
-
-  // ---- colour + opacity (spherical_harmonics.py:36-71, rasterize.py:358) ----
-  float dx, dy, dz;
-  view_direction(p, cam.cam_center, dx, dy, dz);
-  float rgb[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) rgb[c] = sh_channel(dx, dy, dz, degree, [&](int k) { return sh[c][k]; });
-  const float opacity = sigmoid_ref(op_logit);
-
-  // Blend record (include/gsr_b200.h).  A = -a/2, C = -c/2, B = -b are exact rescalings of the reference's conic,
-  // so power = (A dx^2 + C dy^2) + (B dx) dy reproduces rasterize.py:280-283 bit for bit.  `thr` is a lower bound
-  // on the power at which alpha = o*exp(power) can exceed 1/255: below it the blend kernel skips the exp.
-  const float thr = opacity > 0.0f ? -logf(255.0f * opacity) - 1e-4f : __int_as_float(0x7f800000);
-  rec[i * 3 + 0] = make_float4(mx, my, fmul(-0.5f, ca), fmul(-0.5f, cc));
-  rec[i * 3 + 1] = make_float4(-cb, thr, opacity, rgb[0]);
-  rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], opacity > 0.0f ? log2f(opacity) : -1e30f, radius);
-  return key;
-}
-
-
-// Persistent grid-stride kernel.  Besides the per-Gaussian outputs it accumulates the four 8-bit digit histograms of
-// the depth keys (the one-sweep sort's global digit counts) in shared memory - the atomics ride on the otherwise
-// idle LSU pipe of this memory-bound kernel - and flushes them once per CTA.
+// Persistent grid-stride kernel, one Gaussian per thread and iteration, three phases:
+//   A  per lane : loads, projection, EWA covariance, radius, tile rect, conic                (rasterize.py:371-420)
+//   B  per warp : exact tile culling of the warp's 32 rects, candidate tiles dealt evenly to the lanes (a lane
+//                 looping over its own rect would make the warp wait for its largest Gaussian)
+//   C  per lane : SH colour + blend record, only for Gaussians that keep at least one tile
+// It also accumulates the four 8-bit digit histograms of the depth keys (global digit counts of the one-sweep
+// sort) in shared memory and flushes them once per CTA.
 __global__ void __launch_bounds__(kPreThreads, 2)
 preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
                   uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
-                  ushort4 *__restrict__ rect_out, float4 *__restrict__ rec, float *__restrict__ cov3d_out,
-                  float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out, float *__restrict__ mean2d_out,
-                  uint32_t *__restrict__ depth_hist) {
+                  ushort4 *__restrict__ rect_out, uint2 *__restrict__ tile_mask, float4 *__restrict__ rec,
+                  float *__restrict__ cov3d_out, float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out,
+                  float *__restrict__ mean2d_out, uint32_t *__restrict__ depth_hist) {
+  constexpr int kWarps = kPreThreads / 32;
   __shared__ uint32_t s_hist[4][256];
+  __shared__ CullGaussian s_cg[kWarps][32];
+  __shared__ int4 s_rect[kWarps][32];      // x0, y0, width, candidate count (0 when the rect is not culled)
+  __shared__ uint32_t s_mask[kWarps][32][2];
+  __shared__ int s_pref[kWarps][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (depth_hist) {
     for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&s_hist[0][0])[k] = 0;
     __syncthreads();
   }
+  const int degree = cam.sh_degree;
+  const int ncoef = (degree + 1) * (degree + 1);
+  const TileGrid tg = make_grid(cam.width, cam.height);
   const int64_t stride = (int64_t)gridDim.x * kPreThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kPreThreads + threadIdx.x; i < g.n; i += stride) {
-    const uint32_t key = preprocess_one(i, g, cam, row_begin, row_end, depth_key, tiles_touched, rect_out, rec,
-                                        cov3d_out, cov2d_out, rect_raw_out, mean2d_out);
-    if (depth_hist) {
+  for (int64_t base = (int64_t)blockIdx.x * kPreThreads + warp * 32; base < g.n; base += stride) {
+    const bool active = base + lane < g.n;                 // the whole warp stays in the loop (phase B is cooperative)
+    const int64_t i = active ? base + lane : g.n - 1;
+
+    // ---- A: loads - everything this Gaussian needs is requested up front (59 independent 4-byte loads) ----
+    float p[3], ls[3], rot[4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
+    for (int c = 0; c < 3; ++c) p[c] = __ldg(g.xyz + i * g.xyz_sn + c * g.xyz_sc);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ls[c] = __ldg(g.log_scales + i * g.scale_sn + c * g.scale_sc);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rot[c] = __ldg(g.rots + i * g.rot_sn + c * g.rot_sc);
+    const float op_logit = __ldg(g.opacity_logit + i * g.opacity_sn);
+    float sh[3][16];
+    const float *shp = g.sh + i * g.sh_sn;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sh[c][k] = (k < ncoef) ? __ldg(shp + k * g.sh_sk + c * g.sh_sc) : 0.0f;
+
+    // ---- A: geometry, rasterize.py:371-420 ----
+    float camp[3], clip[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) camp[c] = row_affine(cam.w2c_t, c, p[0], p[1], p[2]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) clip[c] = row_affine(cam.full_t, c, p[0], p[1], p[2]);
+    const bool culled = camp[2] < 0.2f;  // :377
+    if (culled) clip[0] = clip[1] = clip[3] = 0.0f;
+    const float pw = frcp(fadd(clip[3], 0.0000001f));  // :381
+    const float mx = fdiv(fsub(fmul(fadd(fmul(clip[0], pw), 1.0f), (float)cam.width), 1.0f), 2.0f);   // :391
+    const float my = fdiv(fsub(fmul(fadd(fmul(clip[1], pw), 1.0f), (float)cam.height), 1.0f), 2.0f);
+    float S[9], c2[4];
+    covariance3d(ls, rot, S);
+    covariance2d(S, camp, cam, c2);
+    if (culled) c2[0] = c2[1] = c2[2] = c2[3] = 0.0f;  // :388
+    float radius;
+    int rr[4];
+    covering_rect(mx, my, c2, cam.width, cam.height, radius, rr);
+    float ca, cc, cb;
+    conic_from_cov(c2, ca, cc, cb);
+    const bool skip = (ca == 0.0f) | (cc == 0.0f) | (cb == 0.0f);  // :441 ("any conic component is zero")
+    const float opacity = sigmoid_ref(op_logit);                    // :358
+    // A = -a/2, C = -c/2, B = -b are exact rescalings of the reference's conic, so
+    // power = (A dx^2 + C dy^2) + (B dx) dy reproduces rasterize.py:280-283 bit for bit.  `thr` is a lower bound on
+    // the power at which alpha = o*exp(power) can exceed 1/255: below it the blend kernel skips the exp.
+    const float A = fmul(-0.5f, ca), C = fmul(-0.5f, cc), B = -cb;
+    const float thr = opacity > 0.0f ? -logf(255.0f * opacity) - 1e-4f : __int_as_float(0x7f800000);
+    // reference tile rect, clipped to the writable tile grid and to this rank's band of tile rows
+    int x0 = min(rr[0], tg.tiles_x_eff), x1 = min(rr[2], tg.tiles_x_eff);
+    int y0 = max(min(rr[1], tg.tiles_y_eff), row_begin), y1 = min(min(rr[3], tg.tiles_y_eff), row_end);
+    const bool blendable = active && !skip && x1 > x0 && y1 > y0;  // the reference's loop would blend it
+
+    // ---- B: drop the (Gaussian, tile) pairs in which no pixel can pass alpha > 1/255 (the image is unchanged) ----
+    // B1 (per lane, free): the pixels that can pass lie in the ellipse power >= limit, whose bounding box is
+    // mean +- sqrt(2 |limit| cov_xx / cov_yy); shrink the reference's 3-sigma SQUARE rect to the tiles under it.
+    const CullGaussian cg = make_cull(mx, my, A, C, B, thr);
+    if (blendable) {
+      const float L = -cg.limit;
+      if (!(L > 0.0f)) {
+        x1 = x0;  // opacity <= 1/255: no pixel ever passes; the rect becomes empty
+      } else if (L < 1e30f) {
+        const float ex = sqrtf(2.0f * L * c2[0]) * 1.0001f + 1e-3f, ey = sqrtf(2.0f * L * c2[3]) * 1.0001f + 1e-3f;
+        x0 = max(x0, (int)floorf((mx - ex) * (1.0f / GSR_TILE)));
+        x1 = min(x1, (int)floorf((mx + ex) * (1.0f / GSR_TILE)) + 1);
+        y0 = max(y0, (int)floorf((my - ey) * (1.0f / GSR_TILE)));
+        y1 = min(y1, (int)floorf((my + ey) * (1.0f / GSR_TILE)) + 1);
+      }
+    }
+    // B2 (per warp): rects of at least 2x2 tiles still have corners the ellipse may miss: exact per-tile test, the
+    // candidate tiles of the warp's 32 rects dealt evenly to the lanes.  (A one-tile-wide strip under the ellipse's
+    // bounding box is always touched, so it needs no test.)
+    x1 = max(x1, x0);  // an emptied rect is stored with zero extent
+    y1 = max(y1, y0);
+    const int w = x1 - x0, h = y1 - y0;
+    const int area = blendable ? w * h : 0;
+    const int cand = (w >= 2 && h >= 2 && area <= kCullMaxTiles) ? area : 0;  // larger rects are kept whole
+    int inc = cand;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    s_pref[warp][lane] = inc - cand;
+    s_rect[warp][lane] = make_int4(x0, y0, w, w > 0 ? (65536 + w - 1) / w : 0);  // .w: 2^16/width rounded up
+    s_cg[warp][lane] = cg;
+    s_mask[warp][lane][0] = 0;
+    s_mask[warp][lane][1] = 0;
+    __syncwarp();
+    {
+      const float xmax = (float)(cam.width - 2), ymax = (float)(cam.height - 2);  // last column / row never written
+      for (int e0 = 0; e0 < total; e0 += 32) {  // warp-uniform trip count: every lane takes part in the votes
+        const bool valid = e0 + lane < total;
+        const int e = valid ? e0 + lane : total - 1;
+        int lo = 0, hi = 31;  // owner: last lane whose exclusive prefix is <= e
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_pref[warp][mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const int4 r = s_rect[warp][lo];
+        const int local = e - s_pref[warp][lo];
+        const int row = (local * r.w) >> 16, col = local - row * r.z;  // exact for local < 64, width <= 64
+        const float px0 = (float)((r.x + col) * GSR_TILE), py0 = (float)((r.y + row) * GSR_TILE);
+        const float px1 = fminf(px0 + (float)(GSR_TILE - 1), xmax), py1 = fminf(py0 + (float)(GSR_TILE - 1), ymax);
+        // Lanes that test candidates of the same owner form one contiguous run of the warp (candidates are ordered by
+        // owner); the first lane of each run ORs the run's keep bits into the owner's mask - no shared atomics.
+        const bool keep = valid && !tile_is_empty(s_cg[warp][lo], px0, py0, px1, py1);
+        const uint32_t kept = __ballot_sync(0xFFFFFFFFu, keep);
+        const int prev_lo = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
+        const uint32_t heads = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev_lo != lo);
+        if ((heads >> lane) & 1u) {
+          const uint32_t later = heads & ~((2u << lane) - 1u);                  // heads after this lane
+          const int end = later ? __ffs(later) - 1 : 32;                         // one past the run's last lane
+          const uint32_t run = (kept >> lane) & ((end - lane) >= 32 ? 0xFFFFFFFFu : ((1u << (end - lane)) - 1u));
+          const unsigned long long bits = (unsigned long long)run << local;     // kept bits of a run fit: local + len <= 64
+          s_mask[warp][lo][0] |= (uint32_t)bits;
+          s_mask[warp][lo][1] |= (uint32_t)(bits >> 32);
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    uint32_t mask_lo = 0xFFFFFFFFu, mask_hi = 0xFFFFFFFFu, tiles = (uint32_t)area;  // untested rects keep every tile
+    if (cand) {
+      mask_lo = s_mask[warp][lane][0];
+      mask_hi = s_mask[warp][lane][1];
+      tiles = (uint32_t)(__popc(mask_lo) + __popc(mask_hi));
+    }
+    __syncwarp();  // shared arrays are rewritten by the next iteration
+
+    const uint32_t key = float_to_key(camp[2]);
+    if (active) {
+      depth_key[i] = key;
+      tiles_touched[i] = tiles | (blendable ? 0x80000000u : 0u);  // bit 31: counted by the reference's loop (:441)
+      rect_out[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+      if (blendable) tile_mask[i] = make_uint2(mask_lo, mask_hi);
+      if (depth_hist) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(&s_hist[q][(key >> (8 * q)) & 255u], 1u);
+      }
+      if (cov3d_out) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cov3d_out[i * 9 + k] = S[k];
+      }
+      if (cov2d_out) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cov2d_out[i * 4 + k] = c2[k];
+      }
+      if (rect_raw_out) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rect_raw_out[i * 4 + k] = rr[k];
+      }
+      if (mean2d_out) {
+        mean2d_out[i * 2] = mx;
+        mean2d_out[i * 2 + 1] = my;
+      }
+    }
+
+    // ---- C: colour (spherical_harmonics.py:36-71) + blend record (include/gsr_b200.h) ----
+    if (active && (tiles != 0 || cov3d_out)) {
+      float dx, dy, dz;
+      view_direction(p, cam.cam_center, dx, dy, dz);
+      float rgb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rgb[c] = sh_channel(dx, dy, dz, degree, [&](int k) { return sh[c][k]; });
+      rec[i * 3 + 0] = make_float4(mx, my, A, C);
+      rec[i * 3 + 1] = make_float4(B, thr, opacity, rgb[0]);
+      rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], opacity > 0.0f ? log2f(opacity) : -1e30f, radius);
     }
   }
   if (depth_hist) {
@@ -228,15 +305,15 @@ static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n
 using namespace gsr;
 
 extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t row_begin, int32_t row_end,
-                                  uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, float *rec,
-                                  float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all,
+                                  uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, uint32_t *tile_mask,
+                                  float *rec, float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all,
                                   uint32_t *depth_hist, void *stream) {
   GSR_REQUIRE(g && cam, "null gaussians/camera");
   GSR_REQUIRE(g->n >= 0 && g->n < (1ll << 31), "n out of range");
   GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
   GSR_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 65535 * GSR_TILE && cam->height <= 65535 * GSR_TILE,
               "image size out of range");
-  GSR_REQUIRE(depth_key && tiles_touched && rect && rec, "null output");
+  GSR_REQUIRE(depth_key && tiles_touched && rect && tile_mask && rec, "null output");
   GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)rect & 7) == 0, "rec must be 16-byte and rect 8-byte aligned");
   if (depth_hist) GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * 1024, (cudaStream_t)stream));
   if (g->n == 0) return GSR_OK;
@@ -244,8 +321,8 @@ extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam,
   const unsigned resident = 148 * 4;  // persistent: a few CTAs per SM, each loops over its share
   if (blocks > resident) blocks = resident;
   preprocess_kernel<<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(
-      *g, *cam, row_begin, row_end, depth_key, tiles_touched, (ushort4 *)rect, (float4 *)rec, cov3d, cov2d,
-      tile_rect_raw, mean2d_all, depth_hist);
+      *g, *cam, row_begin, row_end, depth_key, tiles_touched, (ushort4 *)rect, (uint2 *)tile_mask, (float4 *)rec, cov3d,
+      cov2d, tile_rect_raw, mean2d_all, depth_hist);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

@@ -123,6 +123,8 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   __shared__ uint32_t s_keys[kSortTile];
   __shared__ uint32_t s_vals[kSortTile];
   __shared__ uint2 s_scan[kRadix / 32];
+  __shared__ uint32_t s_part[2][kRadix];
+  __shared__ uint32_t s_open[kRadix];
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,7 +163,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
   __syncthreads();
 
-  // ---- thread d (< 256) owns digit d: counts over warps -> exclusive, tile count, look-back ----
+  // ---- thread d (< 256) owns digit d: counts over warps -> exclusive, tile count ----
   uint32_t count = 0;
   if (tid < kRadix) {
 #pragma unroll
@@ -172,36 +174,61 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
   }
   const uint2 ex = block_exclusive_scan2(make_uint2(count, tid < kRadix ? __ldg(hist + tid) : 0u), s_scan);
-  if (tid < kRadix) {
-    s_excl[tid] = ex.x;
-    uint32_t prefix = 0;
-    uint32_t *my_status = status + (size_t)tile * kRadix + tid;
-    if (tile == 0) {
-      st_volatile_u32(my_status, kFlagInclusive | count);
-    } else {
-      st_volatile_u32(my_status, kFlagAggregate | count);
-      // Decoupled look-back, kLookWindow predecessors per round trip: the loads of a window are independent, so
-      // a walk over w tiles costs ~w/kLookWindow L2 latencies instead of w.
-      constexpr int kLookWindow = 8;
-      int64_t prev = (int64_t)tile - 1;
-      bool open = true;
-      while (open) {
-        uint32_t v[kLookWindow];
-#pragma unroll
-        for (int i = 0; i < kLookWindow; ++i)
-          v[i] = (prev - i >= 0) ? ld_volatile_u32(status + (size_t)(prev - i) * kRadix + tid) : kFlagInclusive;
-#pragma unroll
-        for (int i = 0; i < kLookWindow; ++i) {
-          if (!open) break;
-          while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(status + (size_t)(prev - i) * kRadix + tid);
-          prefix += v[i] & kValueMask;
-          if (v[i] & kFlagInclusive) open = false;
-        }
-        prev -= kLookWindow;
-      }
-      st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
+
+  // ---- decoupled look-back, 32 predecessor tiles per round trip ----
+  // A serial walk costs one L2 latency per tile, and the CTAs of the first wave must walk back over every tile
+  // ahead of them.  Here the two halves of the CTA each fetch 16 predecessors of digit d with independent loads
+  // (coalesced: consecutive threads read consecutive digits of one tile), fold them in order up to the first
+  // inclusive entry, and the halves are combined through shared memory.
+  {
+    const int d = tid & (kRadix - 1), half = tid >> 8;
+    uint32_t *my_status = status + (size_t)tile * kRadix + d;
+    if (half == 0) {
+      s_excl[d] = ex.x;
+      st_volatile_u32(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
+      s_open[d] = tile != 0;
     }
-    s_gbase[tid] = ex.y + prefix - ex.x;
+    uint32_t prefix = 0;
+    int64_t prev = (int64_t)tile - 1;
+    while (true) {
+      __syncthreads();
+      const bool open = s_open[d] != 0;
+      if (__syncthreads_or(open) == 0) break;
+      uint32_t part = 0, found = 0;
+      if (open) {
+        constexpr int kWin = 16;
+        const int64_t first = prev - (int64_t)half * kWin;
+        uint32_t v[kWin];
+#pragma unroll
+        for (int i = 0; i < kWin; ++i)
+          v[i] = (first - i >= 0) ? ld_volatile_u32(status + (size_t)(first - i) * kRadix + d) : kFlagInclusive;
+#pragma unroll
+        for (int i = 0; i < kWin; ++i) {
+          if (found) break;
+          while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(status + (size_t)(first - i) * kRadix + d);
+          part += v[i] & kValueMask;
+          found = v[i] >> 31;  // kFlagInclusive
+        }
+      }
+      s_part[half][d] = part | (found << 31);
+      __syncthreads();
+      if (half == 0 && open) {
+        const uint32_t p0 = s_part[0][d];
+        prefix += p0 & 0x7FFFFFFFu;
+        bool done = p0 >> 31;
+        if (!done) {
+          const uint32_t p1 = s_part[1][d];
+          prefix += p1 & 0x7FFFFFFFu;
+          done = p1 >> 31;
+        }
+        if (done) s_open[d] = 0;
+      }
+      prev -= 32;
+    }
+    if (half == 0) {
+      if (tile != 0) st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
+      s_gbase[d] = ex.y + prefix - ex.x;
+    }
   }
   __syncthreads();
 

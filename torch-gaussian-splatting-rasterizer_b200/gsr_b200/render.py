@@ -200,6 +200,7 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
     out = dict(depth_key=torch.empty(n, dtype=torch.int32, device=dev),
                tiles_touched=torch.empty(n, dtype=torch.int32, device=dev),
                rect=torch.empty((n, 4), dtype=torch.int16, device=dev),
+               tile_mask=torch.zeros((n, 2), dtype=torch.int32, device=dev),
                rec=torch.zeros((n, _cabi.REC_FLOATS), dtype=torch.float32, device=dev),
                depth_hist=torch.empty(1024, dtype=torch.int32, device=dev))
     if debug:
@@ -209,7 +210,7 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
                    mean2d=torch.empty((n, 2), dtype=torch.float32, device=dev))
     g = model.c_struct()
     _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), rb, re, _cabi.ptr(out["depth_key"]),
-               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["rect"]), _cabi.ptr(out["rec"]),
+               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["rect"]), _cabi.ptr(out["tile_mask"]), _cabi.ptr(out["rec"]),
                _cabi.ptr(out.get("cov3d")), _cabi.ptr(out.get("cov2d")), _cabi.ptr(out.get("tile_rect")),
                _cabi.ptr(out.get("mean2d")), _cabi.ptr(out["depth_hist"]), _cabi.stream_handle())
     return out
@@ -242,7 +243,7 @@ def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: in
                tile_ranges=torch.empty((tiles, 2), dtype=torch.int32, device=dev),
                info=torch.zeros(8, dtype=torch.int32, device=dev))
     _cabi.call("gsr_bin", n, _cabi.ptr(pre["depth_key"]), _cabi.ptr(pre.get("depth_hist")),
-               _cabi.ptr(pre["tiles_touched"]), _cabi.ptr(pre["rect"]),
+               _cabi.ptr(pre["tiles_touched"]), _cabi.ptr(pre["rect"]), _cabi.ptr(pre["tile_mask"]),
                width, height, max_dup, _cabi.ptr(out["order"]), _cabi.ptr(out["blend_rank"]),
                _cabi.ptr(out["tile_gids"]), _cabi.ptr(out["tile_ranges"]), _cabi.ptr(out["info"]), _cabi.ptr(ws),
                ws.numel(), _cabi.stream_handle())
