@@ -234,7 +234,7 @@ def main():
             done = torch.cuda.Event(); done.record()
             comm.wait_event(done)
             with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered, buf)
+                dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1))
                 gathered_ev[i % 2] = torch.cuda.Event(); gathered_ev[i % 2].record()
 
     # reserve workspace (one checked frame also validates max_dup)
