@@ -163,6 +163,30 @@ int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const uint32_t *t
                   gsr_frame_info *info_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Backward (the reference has none: the contract is torch.autograd through its forward, :255-305, :371-420 and
+ * spherical_harmonics.py:27-73)
+ * --------------------------------------------------------------------------------------------- */
+/* Blend backward: the tile lists replayed back to front.  final_T / n_contrib are the forward's outputs,
+ * dL_dimage[H,W,3] the incoming gradient; grad_rec[n,9] (zeroed by the caller) accumulates per Gaussian
+ * d mean2d.xy, d conic (a,c,b), d opacity (activated), d rgb. */
+int gsr_blend_bwd(const float *rec, const uint32_t *tile_gids, const uint32_t *tile_ranges, int32_t width,
+                  int32_t height, int32_t tile_row_begin, int32_t tile_row_end, const float *final_T,
+                  const uint32_t *n_contrib, const float *dL_dimage, float *grad_rec, void *stream);
+/* Preprocess + SH backward: grad_rec -> gradients of the raw parameters (contiguous [n,3], [n,3], [n,4], [n]);
+ * d_sh is written with the given element strides ([n,16,3] logical, e.g. the strides of the sh input). */
+int gsr_preprocess_bwd(const gsr_gaussians *g, const gsr_camera *cam, const uint32_t *tiles_touched,
+                       const float *grad_rec, float *d_xyz, float *d_log_scales, float *d_rots, float *d_opacity_logit,
+                       float *d_sh, int64_t dsh_sn, int64_t dsh_sk, int64_t dsh_sc, void *stream);
+/* Whole-frame backward.  Must follow gsr_render_fwd of the same frame with the same, untouched workspace.
+ * grad_rec[n,9] is scratch.  In band mode every rank produces PARTIAL gradients (its band's pixels only); their
+ * sum over the ranks is the full gradient. */
+int gsr_render_bwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                   size_t workspace_bytes, const float *final_T, const uint32_t *n_contrib, const float *dL_dimage,
+                   float *grad_rec, float *d_xyz, float *d_log_scales, float *d_rots, float *d_opacity_logit,
+                   float *d_sh, int64_t dsh_sn, int64_t dsh_sk, int64_t dsh_sc, int32_t tile_row_begin,
+                   int32_t tile_row_end, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Drop-in helpers behind the reference's module-level functions
  * --------------------------------------------------------------------------------------------- */
 /* get_covariance_matrix_from_mesh (:89-120): cov3d[n,3,3]. */

@@ -160,6 +160,32 @@ extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int
                        stream);
 }
 
+// Gradients of one frame.  Must follow gsr_render_fwd of the SAME frame with the SAME workspace (the records and
+// tile lists of the forward pass are replayed, not rebuilt).
+extern "C" int gsr_render_bwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                              size_t workspace_bytes, const float *final_T, const uint32_t *n_contrib,
+                              const float *dL_dimage, float *grad_rec, float *d_xyz, float *d_log_scales, float *d_rots,
+                              float *d_opacity_logit, float *d_sh, int64_t dsh_sn, int64_t dsh_sk, int64_t dsh_sc,
+                              int32_t tile_row_begin, int32_t tile_row_end, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GSR_REQUIRE(g && cam && workspace && final_T && n_contrib && dL_dimage && grad_rec, "null pointer");
+  FrameLayout L;
+  int rc = frame_layout(g->n, cam->width, cam->height, max_dup, &L);
+  if (rc) return rc;
+  if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+    set_error("render workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
+    return GSR_ERR_WORKSPACE_TOO_SMALL;
+  }
+  char *ws = (char *)workspace;
+  GSR_CHECK_CUDA(cudaMemsetAsync(grad_rec, 0, sizeof(float) * 9 * (size_t)(g->n > 0 ? g->n : 1), stream));
+  rc = gsr_blend_bwd((const float *)(ws + L.rec), (const uint32_t *)(ws + L.tile_gids),
+                     (const uint32_t *)(ws + L.tile_ranges), cam->width, cam->height, tile_row_begin, tile_row_end,
+                     final_T, n_contrib, dL_dimage, grad_rec, stream);
+  if (rc) return rc;
+  return gsr_preprocess_bwd(g, cam, (const uint32_t *)(ws + L.tiles_touched), grad_rec, d_xyz, d_log_scales, d_rots,
+                            d_opacity_logit, d_sh, dsh_sn, dsh_sk, dsh_sc, stream);
+}
+
 // Host-buffer frame: stands where the body of the reference's run_rasterization stands (rasterize.py:354-452).
 extern "C" int gsr_render_host(const gsr_gaussians *gh, const gsr_camera *cam, int64_t max_dup, float *image_host,
                                gsr_frame_info *info_host) {

@@ -23,13 +23,10 @@
 // pixel is parked at y = 1e18 so that it fails the test without costing an extra instruction.
 #include <stdlib.h>
 
-#include "gsr_common.cuh"
+#include "blend_common.cuh"
 
 namespace gsr {
 
-constexpr float kMinAlpha = (float)(1.0 / 255.0);   // MIN_ALPHA, rasterize.py:38 (compared in f32 like torch does)
-constexpr float kMaxDensity = 0.99f;                // MAX_GAUSSIAN_DENSITY, rasterize.py:36
-constexpr float kStopT = 1e-4f;
 constexpr float kParkedY = 1e18f;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -37,11 +34,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -164,12 +156,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
 #pragma unroll
           for (int k = 0; k < PX; ++k) {
             if (power[k] >= w.y) {
-              // alpha = min(o*exp(power), 0.99) (:285-288) as one FFMA + MUFU.EX2.  Its VALUE may differ from the
-              // reference's by a few 1e-7 (continuous, harmless); the DECISION alpha > 1/255 (:291) is discontinuous,
-              // so inside a +-1e-5 band around the threshold it is re-taken with the reference's own arithmetic.
-              float alpha = fminf(ex2_approx(fmaf(power[k], 1.4426950408889634f, gbl.z)), kMaxDensity);
-              if (fabsf(fmaf(alpha, 255.0f, -1.0f)) < 1e-5f) alpha = fminf(fmul(orr.x, expf(power[k])), kMaxDensity);
-              if (alpha > kMinAlpha && power[k] <= 0.0f) {
+              float alpha;
+              if (blend_alpha(power[k], orr.x, gbl.z, alpha)) {
                 const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
                 C0[k] = fmaf(wgt, orr.y, C0[k]);
                 C1[k] = fmaf(wgt, gbl.x, C1[k]);

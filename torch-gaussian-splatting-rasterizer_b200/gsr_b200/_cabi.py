@@ -64,6 +64,13 @@ PROTOTYPES = {
                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "gsr_blend_fwd": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_uint32, c_uint32,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "gsr_blend_bwd": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_void_p],
+    "gsr_preprocess_bwd": [POINTER(Gaussians), POINTER(CameraStruct), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "gsr_render_bwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, c_size_t, c_void_p, c_void_p,
+                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                       c_int32, c_int32, c_void_p],
     "gsr_cov3d_fwd": [c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
     "gsr_quat_to_rotmat": [c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
     "gsr_affine_fwd": [c_int64, c_void_p, c_int64, c_int64, POINTER(c_float), c_int32, c_void_p, c_void_p],

@@ -102,6 +102,7 @@ class Renderer:
         self._ws_key = None
         self.max_dup = 0
         self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)  # gsr_frame_info (32 bytes)
+        self.frame_serial = 0  # bumped by every frame: backward must replay the workspace of ITS forward
 
     # -- workspace ---------------------------------------------------------------------------
     def reserve(self, n: int, width: int, height: int, max_dup: Optional[int] = None) -> None:
@@ -130,6 +131,7 @@ class Renderer:
         assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (H, W, 3)
         rb, re = (0, -1) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
         while True:
+            self.frame_serial += 1
             ws = _align256(self._ws)
             g = model.c_struct()
             _cabi.call("gsr_render_fwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws),
@@ -150,6 +152,65 @@ class Renderer:
         raw = self.info_dev.cpu().numpy().view(np.uint32)
         return dict(status=int(raw[0]), n_visible=int(raw[1]), n_dup=int(raw[2]),
                     warp_evals=int(raw[4]) | (int(raw[5]) << 32), pixel_evals=int(raw[6]) | (int(raw[7]) << 32))
+
+
+    def backward(self, model: GaussianModel, cam: CameraStruct, final_T: torch.Tensor, n_contrib: torch.Tensor,
+                 grad_image: torch.Tensor, tile_rows: Optional[Sequence[int]] = None):
+        """Gradients of the last frame rendered with this renderer (same model, same camera)."""
+        n, dev = model.n, self.device
+        grad_image = grad_image.contiguous().float()
+        scratch = torch.empty((max(n, 1), 9), dtype=torch.float32, device=dev)
+        d_xyz = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        d_ls = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        d_rot = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        d_op = torch.empty((n,), dtype=torch.float32, device=dev)
+        d_sh = torch.empty_strided(tuple(model.sh.shape), model.sh.stride(), dtype=torch.float32, device=dev)
+        rb, re = (0, -1) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+        ws = _align256(self._ws)
+        g = model.c_struct()
+        _cabi.call("gsr_render_bwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws), ws.numel(),
+                   _cabi.ptr(final_T), _cabi.ptr(n_contrib), _cabi.ptr(grad_image), _cabi.ptr(scratch), _cabi.ptr(d_xyz),
+                   _cabi.ptr(d_ls), _cabi.ptr(d_rot), _cabi.ptr(d_op), _cabi.ptr(d_sh), *d_sh.stride(), rb, re,
+                   _cabi.stream_handle())
+        return d_xyz, d_ls, d_rot, d_op, d_sh
+
+
+class _RenderFunction(torch.autograd.Function):
+    """image = render(parameters): forward through gsr_render_fwd, backward through gsr_render_bwd."""
+
+    @staticmethod
+    def forward(ctx, xyz, log_scales, rots, opacity, sh, renderer, cam, tile_rows):
+        model = GaussianModel(xyz.detach(), log_scales.detach(), rots.detach(), opacity.detach(), sh.detach())
+        H, W = cam.height, cam.width
+        final_T = torch.empty((H, W), dtype=torch.float32, device=renderer.device)
+        n_contrib = torch.zeros((H, W), dtype=torch.int32, device=renderer.device)
+        out = torch.zeros((H, W, 3), dtype=torch.float32, device=renderer.device)
+        image = renderer.render(model, cam, out=out, final_T=final_T, n_contrib=n_contrib, tile_rows=tile_rows)
+        ctx.model, ctx.renderer, ctx.cam, ctx.tile_rows = model, renderer, cam, tile_rows
+        ctx.serial = renderer.frame_serial
+        ctx.save_for_backward(final_T, n_contrib)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        if ctx.renderer.frame_serial != ctx.serial:
+            raise RuntimeError("the renderer drew another frame since this forward pass: its workspace (records, tile "
+                               "lists) was overwritten; call backward before rendering again or use one Renderer per graph")
+        final_T, n_contrib = ctx.saved_tensors
+        grads = ctx.renderer.backward(ctx.model, ctx.cam, final_T, n_contrib, grad_image, ctx.tile_rows)
+        return (*grads, None, None, None)
+
+
+def render_differentiable(xyz, log_scales, rots, opacity_logits, sh, cam: CameraStruct,
+                          renderer: Optional[Renderer] = None, tile_rows=None) -> torch.Tensor:
+    """Differentiable frame: CUDA float32 tensors in (raw 3DGS parameters, sh [N,16,3] any strides), image out."""
+    _cabi.require_cuda()
+    r = renderer or default_renderer()
+    for t in (xyz, log_scales, rots, opacity_logits, sh):
+        if not (t.is_cuda and t.dtype == torch.float32):
+            raise ValueError("render_differentiable needs CUDA float32 tensors")
+    return _RenderFunction.apply(xyz.contiguous(), log_scales.contiguous(), rots.contiguous(),
+                                 opacity_logits.contiguous(), sh, r, cam, tile_rows)
 
 
 _default_renderer: Optional[Renderer] = None
