@@ -129,14 +129,23 @@ def test_binning_equals_stable_sort_of_tile_depth_keys(name, golden, R):
     # blend rank = position among the Gaussians the reference's loop blends
     blended = o["order"][o["skip"][o["order"]] == 0]
     assert np.array_equal(binned["blend_rank"].cpu().numpy()[blended], np.arange(blended.shape[0]))
+    # the bucket path (atomic cursors + on-chip sort of every tile's segment) builds exactly the same lists
+    for counted in (False, True):  # list lengths counted by gsr_bin itself / by the preprocess kernel
+        pre_b = R.preprocess(model, cam, count_tiles=counted)
+        fast = R.bin_tiles(pre_b, cam.width, cam.height, max_dup=max(1024, 2 * tile.shape[0]), ordered=False)
+        finfo = fast["info"].cpu().numpy().view(np.uint32)
+        assert finfo[0] == 0 and finfo[1] == info[1] and finfo[2] == n_dup
+        assert np.array_equal(fast["tile_ranges"].cpu().numpy(), binned["tile_ranges"].cpu().numpy())
+        assert np.array_equal(fast["tile_gids"].cpu().numpy()[:n_dup], binned["tile_gids"].cpu().numpy()[:n_dup])
 
 
 def test_binning_overflow_is_flagged(R):
     cloud, intr, view, cam = _case("synth_small")
     pre = R.preprocess(R.GaussianModel.from_cloud(cloud), cam)
-    binned = R.bin_tiles(pre, cam.width, cam.height, max_dup=1000)
-    info = binned["info"].cpu().numpy().view(np.uint32)
-    assert info[0] == 4 and info[2] > 1000  # GSR_ERR_DUP_OVERFLOW and the size that would have been needed
+    for ordered in (True, False):
+        binned = R.bin_tiles(pre, cam.width, cam.height, max_dup=1000, ordered=ordered)
+        info = binned["info"].cpu().numpy().view(np.uint32)
+        assert info[0] == 4 and info[2] > 1000  # GSR_ERR_DUP_OVERFLOW and the size that would have been needed
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -182,7 +182,8 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
 constexpr int kOffsThreads = 1024;
 __global__ void __launch_bounds__(kOffsThreads)
 tile_offsets_kernel(const uint32_t *__restrict__ tile_count, int num_tiles, uint2 *__restrict__ ranges,
-                    uint32_t *__restrict__ hist /*[passes][256]*/, int passes, uint32_t last_mask) {
+                    uint32_t *__restrict__ hist /*[passes][256]*/, int passes, uint32_t last_mask, uint32_t capacity,
+                    BinCounters *ctr, gsr_frame_info *info) {
   __shared__ uint32_t s_warp[kOffsThreads / 32];
   __shared__ uint32_t s_hist[2][256];
   __shared__ uint32_t s_carry;
@@ -214,19 +215,151 @@ tile_offsets_kernel(const uint32_t *__restrict__ tile_count, int num_tiles, uint
     if (tid == kOffsThreads - 1) s_carry = pre + inc;
     __syncthreads();
   }
-  if (tid < 256) {
-    hist[tid] = passes == 1 ? 0u : s_hist[0][tid];
+  if (passes > 0 && tid < 256) {
+    hist[tid] = s_hist[0][tid];
     if (passes > 1) hist[256 + tid] = s_hist[1][tid];
   }
-  if (passes == 1 && tid < 256) {  // single pass: the (masked) low digit is the whole key
-    // recompute with the mask applied: tiles < 256 here, so t & 255 & last_mask == t
-    hist[tid] = s_hist[0][tid];
+  if (ctr) {  // bucket path: this kernel is the first to know the number of pairs
+    const uint32_t total = s_carry;
+    const bool overflow = total > capacity;
+    if (overflow)  // no list may point past the pair buffer: the frame is flagged and drawn empty
+      for (int t = tid; t < num_tiles; t += kOffsThreads) ranges[t] = make_uint2(0u, 0u);
+    if (tid == 0) {
+      ctr->n_dup = overflow ? 0u : total;
+      if (info) {
+        info->n_dup = total;
+        if (overflow) info->status = GSR_ERR_DUP_OVERFLOW;
+      }
+    }
+  }
+}
+
+// ---- bucket path (frames without a rank window) ---------------------------------------------------------------
+// With the list length of every tile known (counted by the preprocess kernel), each (Gaussian, tile) pair can be
+// dropped straight into its tile's segment through an atomic cursor - no global depth sort, no scan - as the
+// 64-bit word (depth key << 32 | Gaussian id).  The segment of a tile is then sorted ON CHIP by that word, which
+// is exactly the order (depth bits, Gaussian index): the arbitrary arrival order of the atomics cannot show.
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads)
+emit_pairs_kernel(int64_t n, const uint32_t *__restrict__ tiles_touched, const ushort4 *__restrict__ rect,
+                  const uint2 *__restrict__ tile_mask, const uint32_t *__restrict__ depth_key,
+                  const uint2 *__restrict__ ranges, uint32_t *__restrict__ cursor, const BinCounters *ctr,
+                  unsigned long long *__restrict__ pairs, int tiles_x) {
+  constexpr int kWarps = kEmitThreads / 32;
+  __shared__ int s_pref[kWarps][33];
+  __shared__ ushort4 s_rect[kWarps][32];
+  __shared__ uint2 s_mask[kWarps][32];
+  __shared__ uint32_t s_key[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stored = ctr->n_dup;  // 0 when the frame overflowed
+  if (stored == 0) return;
+  const int64_t stride = (int64_t)gridDim.x * kEmitThreads;
+  for (int64_t base = (int64_t)blockIdx.x * kEmitThreads + warp * 32; base < n; base += stride) {
+    const int64_t i = base + lane;
+    const int cnt = i < n ? (int)(__ldg(tiles_touched + i) & 0x7FFFFFFFu) : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    if (total == 0) continue;
+    __syncwarp();
+    s_pref[warp][lane] = inc - cnt;
+    if (cnt) {
+      s_rect[warp][lane] = __ldg(rect + i);
+      s_mask[warp][lane] = __ldg(tile_mask + i);
+      s_key[warp][lane] = __ldg(depth_key + i);
+    }
+    __syncwarp();
+    for (int e = lane; e < total; e += 32) {
+      int lo = 0, hi = 31;
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pref[warp][mid] <= e) lo = mid; else hi = mid - 1;
+      }
+      const ushort4 r = s_rect[warp][lo];
+      uint32_t local = (uint32_t)(e - s_pref[warp][lo]);
+      const uint32_t w = (uint32_t)(r.z - r.x);
+      if (w * (uint32_t)(r.w - r.y) <= (uint32_t)kCullMaxTiles) {
+        const uint2 km = s_mask[warp][lo];
+        local = nth_set_bit(km.x, km.y, local);
+      }
+      const uint32_t row = local / w, col = local - row * w;
+      const uint32_t tile = (r.y + row) * (uint32_t)tiles_x + r.x + col;
+      const uint32_t slot = __ldg(&ranges[tile].x) + atomicAdd(cursor + tile, 1u);
+      if (slot < stored) pairs[slot] = ((unsigned long long)s_key[warp][lo] << 32) | (uint32_t)(base + lo);
+    }
+  }
+}
+
+// Bitonic sort of one tile's segment, every compare-exchange ascending (the first step of each merge mirrors the
+// block instead of reversing a direction), so positions >= n behave as +infinity without being stored and any
+// length works.  GLOBAL = false: segment staged in shared memory; true: sorted in place in global memory (lists
+// too long for shared memory - slow but complete).
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS)
+tile_sort_kernel(const uint2 *__restrict__ ranges, unsigned long long *pairs, uint32_t *__restrict__ tile_gids,
+                 int num_tiles, uint32_t min_len, uint32_t max_len) {
+  extern __shared__ unsigned long long s_seg[];
+  const int tid = threadIdx.x;
+  // grid-stride over tiles: the short-list class is launched with one CTA per tile, the long-list classes with a
+  // few resident CTAs that skim the range table for their (rare) members
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint2 r = ranges[tile];
+    const uint32_t n = r.y - r.x;
+    if (n < min_len || n > max_len) continue;  // another launch owns this length class (uniform per CTA)
+    unsigned long long *seg = GLOBAL ? pairs + r.x : s_seg;
+    if (!GLOBAL) {
+      for (uint32_t i = tid; i < n; i += THREADS) seg[i] = pairs[r.x + i];
+    }
+    __syncthreads();
+    for (uint32_t lk = 1; (1u << (lk - 1)) < n; ++lk) {       // merge blocks of k = 2^lk
+      for (int lj = (int)lk - 1; lj >= 0; --lj) {              // compare distance j = 2^lj
+        const uint32_t j = 1u << lj, kmask = (1u << lk) - 1u;
+        const bool mirror = lj == (int)lk - 1;
+        for (uint32_t c = tid;; c += THREADS) {
+          const uint32_t i = ((c >> lj) << (lj + 1)) | (c & (j - 1));  // lower element of compare-exchange c
+          if (i >= n) break;
+          const uint32_t p = mirror ? (i ^ kmask) : (i | j);
+          if (p < n) {
+            const unsigned long long a = seg[i], b = seg[p];
+            if (a > b) {
+              seg[i] = b;
+              seg[p] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (uint32_t i = tid; i < n; i += THREADS) tile_gids[r.x + i] = (uint32_t)seg[i];
+    __syncthreads();  // the segment buffer is reused by the next tile of this CTA
+  }
+}
+
+// list lengths when the preprocess kernel did not count them (stand-alone use of gsr_bin)
+__global__ void count_tiles_kernel(int64_t n, const uint32_t *__restrict__ tiles_touched, const ushort4 *__restrict__ rect,
+                                   const uint2 *__restrict__ tile_mask, uint32_t *__restrict__ tile_count, int tiles_x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t cnt = __ldg(tiles_touched + i) & 0x7FFFFFFFu;
+  if (!cnt) return;
+  const ushort4 r = __ldg(rect + i);
+  const uint32_t w = (uint32_t)(r.z - r.x), area = w * (uint32_t)(r.w - r.y);
+  const uint2 km = area <= (uint32_t)kCullMaxTiles ? __ldg(tile_mask + i) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+  for (uint32_t k = 0; k < cnt; ++k) {
+    const uint32_t local = area <= (uint32_t)kCullMaxTiles ? nth_set_bit(km.x, km.y, k) : k;
+    const uint32_t row = local / w, col = local - row * w;
+    atomicAdd(tile_count + (r.y + row) * (uint32_t)tiles_x + r.x + col, 1u);
   }
 }
 
 struct BinLayout {
-  size_t counters, scan_status, tile_count, tile_hist, depth_sort, tile_sort, dkeys_tmp, dkeys_out, dvals_tmp, tkeys_a,
-      tkeys_b, tkeys_c, tgids_a, tgids_b, total;
+  size_t counters, scan_status, tile_count, tile_cursor, tile_hist, depth_sort, tile_sort, dkeys_tmp, dkeys_out, dvals_tmp, tkeys_a,
+      tkeys_b, tkeys_c, tgids_a, tgids_b, pairs, total;
 };
 
 static BinLayout bin_layout(int64_t n, int64_t max_dup, int num_tiles) {
@@ -241,6 +374,7 @@ static BinLayout bin_layout(int64_t n, int64_t max_dup, int num_tiles) {
   L.counters = take(sizeof(BinCounters));
   L.scan_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kScanTile));
   L.tile_count = take(sizeof(uint32_t) * (size_t)(num_tiles > 0 ? num_tiles : 1));
+  L.tile_cursor = take(sizeof(uint32_t) * (size_t)(num_tiles > 0 ? num_tiles : 1));
   L.tile_hist = take(sizeof(uint32_t) * 4 * 256);
   L.depth_sort = take(sort_scratch_bytes(n1));
   L.tile_sort = take(sort_scratch_bytes(d1));
@@ -252,6 +386,7 @@ static BinLayout bin_layout(int64_t n, int64_t max_dup, int num_tiles) {
   L.tkeys_c = take(4 * (size_t)d1);
   L.tgids_a = take(4 * (size_t)d1);
   L.tgids_b = take(4 * (size_t)d1);
+  L.pairs = take(8 * (size_t)d1);
   L.total = off;
   return L;
 }
@@ -267,14 +402,31 @@ extern "C" int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height,
   return GSR_OK;
 }
 
+static int launch_tile_sorts(const uint2 *ranges, unsigned long long *pairs, uint32_t *tile_gids, int num_tiles,
+                             cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    GSR_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        16384 * 8));
+    configured = true;
+  }
+  // one launch per length class; a CTA whose tile belongs to another class retires at once
+  tile_sort_kernel<256, false><<<num_tiles, 256, 1024 * 8, stream>>>(ranges, pairs, tile_gids, num_tiles, 1u, 1024u);
+  tile_sort_kernel<512, false><<<148 * 2, 512, 4096 * 8, stream>>>(ranges, pairs, tile_gids, num_tiles, 1025u, 4096u);
+  tile_sort_kernel<1024, false><<<148, 1024, 16384 * 8, stream>>>(ranges, pairs, tile_gids, num_tiles, 4097u, 16384u);
+  tile_sort_kernel<1024, true><<<148, 1024, 0, stream>>>(ranges, pairs, tile_gids, num_tiles, 16385u, 0xFFFFFFFFu);
+  GSR_LAUNCH_CHECK();
+  return GSR_OK;
+}
+
 extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
-                       const uint16_t *rect, const uint32_t *tile_mask, int32_t width, int32_t height, int64_t max_dup,
-                       uint32_t *depth_order,
-                       uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
-                       void *workspace, size_t workspace_bytes, void *stream_) {
+                       const uint16_t *rect, const uint32_t *tile_mask, const uint32_t *tile_count_in, int32_t width,
+                       int32_t height, int64_t max_dup, uint32_t *depth_order, uint32_t *blend_rank, uint32_t *tile_gids,
+                       uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace, size_t workspace_bytes,
+                       void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  GSR_REQUIRE(depth_key && tiles_touched && rect && tile_mask && depth_order && tile_gids && tile_ranges && workspace,
-              "null pointer");
+  GSR_REQUIRE(depth_key && tiles_touched && rect && tile_mask && tile_gids && tile_ranges && workspace, "null pointer");
+  GSR_REQUIRE((depth_order == nullptr) == (blend_rank == nullptr) || depth_order, "blend_rank needs depth_order");
   GSR_REQUIRE(n >= 0 && n < (1ll << 30) && max_dup > 0 && max_dup < (1ll << 30), "n / max_dup out of range");
   GSR_REQUIRE(width > 0 && height > 0, "bad image size");
   const TileGrid tg = make_grid(width, height);
@@ -288,13 +440,35 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   BinCounters *ctr = (BinCounters *)(ws + L.counters);
   unsigned long long *scan_status = (unsigned long long *)(ws + L.scan_status);
   uint32_t *tile_count = (uint32_t *)(ws + L.tile_count), *tile_hist = (uint32_t *)(ws + L.tile_hist);
-  // counters + scan status + tile counts + tile digit histograms are contiguous: one memset
+  // counters + scan status + tile counts + cursors + tile digit histograms are contiguous: one memset
   GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.depth_sort - L.counters, stream));
   if (n == 0) {
     GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
     return GSR_OK;
   }
 
+  if (!depth_order) {
+    // ---- bucket path: no global depth order wanted (every frame without a rank window) ----
+    const uint32_t *counts = tile_count_in;
+    if (!counts) {
+      count_tiles_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(n, tiles_touched, (const ushort4 *)rect,
+                                                                        (const uint2 *)tile_mask, tile_count, tg.tiles_x);
+      GSR_LAUNCH_CHECK();
+      counts = tile_count;
+    }
+    tile_offsets_kernel<<<1, kOffsThreads, 0, stream>>>(counts, num_tiles, (uint2 *)tile_ranges, tile_hist, 0, 0u,
+                                                        (uint32_t)max_dup, ctr, info_dev);
+    GSR_LAUNCH_CHECK();
+    unsigned long long *pairs = (unsigned long long *)(ws + L.pairs);
+    int64_t want = ceil_div64(n, kEmitThreads);
+    emit_pairs_kernel<<<(unsigned)(want > 148 * 16 ? 148 * 16 : want), kEmitThreads, 0, stream>>>(
+        n, tiles_touched, (const ushort4 *)rect, (const uint2 *)tile_mask, depth_key, (const uint2 *)tile_ranges,
+        (uint32_t *)(ws + L.tile_cursor), ctr, pairs, tg.tiles_x);
+    GSR_LAUNCH_CHECK();
+    return launch_tile_sorts((const uint2 *)tile_ranges, pairs, tile_gids, num_tiles, stream);
+  }
+
+  // ---- ordered path: also yields the global depth order / blend ranks (rank-windowed frames) ----
   // 1. global depth order (ties by Gaussian index); digit counts come from the preprocess kernel when available
   SortScratch s1, s2;
   int rc = sort_scratch_carve(ws + L.depth_sort, L.tile_sort - L.depth_sort, n, &s1);
@@ -307,8 +481,7 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
   scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, 0, stream>>>(
       n, depth_order, tiles_touched, (const ushort4 *)rect, (const uint2 *)tile_mask, tg.tiles_x, (uint32_t)max_dup,
-      scan_status, ctr, tkeys_a,
-      tgids_a, blend_rank, tile_count, info_dev);
+      scan_status, ctr, tkeys_a, tgids_a, blend_rank, tile_count, info_dev);
   GSR_LAUNCH_CHECK();
 
   // 3. tile ranges and the digit histograms of the tile sort, both from the list lengths
@@ -318,7 +491,7 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   const int passes = (tile_bits + 7) / 8;
   const uint32_t last_mask = (1u << (tile_bits - 8 * (passes - 1))) - 1u;
   tile_offsets_kernel<<<1, kOffsThreads, 0, stream>>>(tile_count, num_tiles, (uint2 *)tile_ranges, tile_hist, passes,
-                                                      last_mask);
+                                                      last_mask, (uint32_t)max_dup, nullptr, nullptr);
   GSR_LAUNCH_CHECK();
 
   // 4. stable sort of the pairs by tile id
