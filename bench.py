@@ -180,13 +180,15 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="frames in flight per GPU: successive steps alternate between this many renderers/streams")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -210,6 +212,8 @@ def main():
     W, H = intr.width, intr.height
     model = R.GaussianModel.from_cloud(cloud)
     renderer = R.Renderer()
+    n_streams = max(1, args.streams)
+    lanes = [(renderer, torch.cuda.current_stream())] + [(R.Renderer(), torch.cuda.Stream()) for _ in range(n_streams - 1)]
     if world == 1:
         views = [scenes.front_view(0)]
     else:
@@ -222,23 +226,42 @@ def main():
     frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world, H, W, 3), dtype=torch.float32, device="cuda") if world > 1 else None
     comm = torch.cuda.Stream() if world > 1 else None
-    frames = [torch.empty_like(frame) for _ in range(2)]
-    gathered_ev = [None, None]
+    n_buf = 2 * n_streams
+    frames = [torch.empty_like(frame) for _ in range(n_buf)]
+    gathered_ev = [None] * n_buf
 
     def step(i):
-        buf = frames[i % 2]
-        if gathered_ev[i % 2] is not None:  # the gather that last read this buffer must have finished
-            torch.cuda.current_stream().wait_event(gathered_ev[i % 2])
-        renderer.render(model, cam_for(i), out=buf, check=False)
-        if world > 1:  # the only collective: gather the finished frames (overlaps with the next render)
-            done = torch.cuda.Event(); done.record()
-            comm.wait_event(done)
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1))
-                gathered_ev[i % 2] = torch.cuda.Event(); gathered_ev[i % 2].record()
+        # Successive frames are independent: frame i runs on lane i % n_streams (own renderer, workspace and stream),
+        # so the latency-bound binning kernels of one frame overlap the issue-bound blend of another.
+        rend, strm = lanes[i % n_streams]
+        buf = frames[i % n_buf]
+        with torch.cuda.stream(strm):
+            if gathered_ev[i % n_buf] is not None:  # the gather that last read this buffer must have finished
+                strm.wait_event(gathered_ev[i % n_buf])
+            rend.render(model, cam_for(i), out=buf, check=False)
+            if world > 1:  # the only collective: gather the finished frames (overlaps with the next render)
+                done = torch.cuda.Event(); done.record(strm)
+                comm.wait_event(done)
+                with torch.cuda.stream(comm):
+                    dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1))
+                    gathered_ev[i % n_buf] = torch.cuda.Event(); gathered_ev[i % n_buf].record(comm)
 
-    # reserve workspace (one checked frame also validates max_dup)
-    renderer.render(model, cams[0], out=frame, check=True)
+    def fork():   # side lanes start after everything already queued on the main stream
+        ev = torch.cuda.Event(); ev.record()
+        for _, strm in lanes[1:]:
+            strm.wait_event(ev)
+
+    def join():   # the main stream waits for every lane (and the gathers)
+        for _, strm in lanes[1:]:
+            torch.cuda.current_stream().wait_stream(strm)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
+
+    # reserve workspaces (one checked frame per lane also validates max_dup)
+    for rend, strm in lanes:
+        with torch.cuda.stream(strm):
+            rend.render(model, cams[0], out=frame, check=True)
+    torch.cuda.synchronize()
     info0 = renderer.frame_info()
     log(f"[bench] rank {rank}: n_visible {info0['n_visible']} n_dup {info0['n_dup']} max_dup {renderer.max_dup}")
 
@@ -247,17 +270,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    fork()
     for i in range(args.warmup):
         step(i)
+    join()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         ev0.record()
+        fork()
         for i in range(args.steps):
             step(args.warmup + i)
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(comm)
+        join()
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -268,7 +293,7 @@ def main():
     ms_per_step = ms / args.steps
     frames_per_s = world * args.steps / (ms / 1e3)
     mpix_s = frames_per_s * W * H / 1e6
-    status_after = renderer.frame_info()["status"]
+    status_after = max(r.frame_info()["status"] for r, _ in lanes)
 
     line = {"metric": "MPix/s, 3M-Gaussian SH3 @1080p render", "value": mpix_s, "unit": "MPix/s", "fps": frames_per_s,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -278,7 +303,8 @@ def main():
                                          f"(rank r renders view step*{world}+r), frames all-gathered with NCCL"),
                        "n_gaussians": cloud.n, "width": W, "height": H, "sh_degree": degree,
                        "l2_policy": "inputs (708 MB of Gaussian parameters) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"view-sharded x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"view-sharded x{world}" if world > 1 else "single GPU",
+                       "frames_in_flight": n_streams},
             "gpu_launches": 12 * args.steps, "frame_status": status_after}
 
     if rank == 0:

@@ -207,6 +207,17 @@ def test_band_renders_tile_rows_independently(R):
     assert torch.equal(out, full)
 
 
+def test_render_views_on_two_lanes_equals_single_renders(R):
+    cloud, intr, view, cam = _case("orbit_a")
+    model = R.GaussianModel.from_cloud(cloud)
+    views = scenes.orbit_views(5, total=16)
+    r = R.Renderer()
+    frames = R.render_views(model, intr, views, 3, renderer=r, lanes=2)
+    torch.cuda.synchronize()
+    for i, v in enumerate(views):
+        assert torch.equal(frames[i], R.Renderer().render(model, camera.camera_for(intr, v, 3)))
+
+
 def test_c1_full_size_against_reference_probe(golden, R):
     """BASELINE.json config 1: 50k random-init Gaussians, 640x420, against the reference's own full render."""
     g = golden("c1_probe")

@@ -94,33 +94,44 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
     if (w < warp) pre += s_warp[w];
     total += s_warp[w];
   }
-  // decoupled look-back (thread 0), broadcast through shared memory
-  if (tid == 0) {
+  // decoupled look-back by warp 0, 32 predecessors per round trip (lane l inspects CTA tile-1-l of the window);
+  // the exclusive prefix is broadcast through shared memory
+  if (warp == 0) {
     unsigned long long prefix = 0;
     if (tile == 0) {
-      st_volatile_u64(status, kScanInclusive | total);
+      if (lane == 0) st_volatile_u64(status, kScanInclusive | total);
     } else {
-      st_volatile_u64(status + tile, kScanAggregate | total);
-      const unsigned long long *look = status + tile - 1;
+      if (lane == 0) st_volatile_u64(status + tile, kScanAggregate | total);
+      int64_t win = (int64_t)tile - 1;  // newest predecessor of the current window
       while (true) {
-        const unsigned long long v = ld_volatile_u64(look);
-        if ((v >> 62) == 0) continue;
-        prefix += v & kScanValue;
-        if (v & kScanInclusive) break;
-        --look;
+        const int64_t mine_idx = win - lane;
+        unsigned long long v = kScanInclusive;  // before tile 0: an inclusive prefix of zero
+        if (mine_idx >= 0) {
+          do { v = ld_volatile_u64(status + mine_idx); } while ((v >> 62) == 0);
+        }
+        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v & kScanInclusive) != 0);
+        const int stop = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix
+        unsigned long long part = lane <= stop ? (v & kScanValue) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        prefix += part;
+        if (incl) break;
+        win -= 32;
       }
-      st_volatile_u64(status + tile, kScanInclusive | (prefix + total));
+      if (lane == 0) st_volatile_u64(status + tile, kScanInclusive | (prefix + total));
     }
-    s_base = prefix;
-    const int64_t tiles_total = (n + kScanTile - 1) / kScanTile;
-    if ((int64_t)tile == tiles_total - 1) {  // last CTA in depth order knows the totals
-      const unsigned long long all = prefix + total;
-      const uint32_t dup = (uint32_t)(all & 0x7FFFFFFFull), vis = (uint32_t)(all >> 31);
-      ctr->n_dup = dup < capacity ? dup : capacity;
-      if (info) {
-        info->n_dup = dup;
-        info->n_visible = vis;
-        if (dup > capacity) info->status = GSR_ERR_DUP_OVERFLOW;
+    if (lane == 0) {
+      s_base = prefix;
+      const int64_t tiles_total = (n + kScanTile - 1) / kScanTile;
+      if ((int64_t)tile == tiles_total - 1) {  // last CTA in depth order knows the totals
+        const unsigned long long all = prefix + total;
+        const uint32_t dup = (uint32_t)(all & 0x7FFFFFFFull), vis = (uint32_t)(all >> 31);
+        ctr->n_dup = dup < capacity ? dup : capacity;
+        if (info) {
+          info->n_dup = dup;
+          info->n_visible = vis;
+          if (dup > capacity) info->status = GSR_ERR_DUP_OVERFLOW;
+        }
       }
     }
   }
