@@ -341,8 +341,15 @@ def main():
         blend_tflops = warp_evals * FLOP_PER_EVAL / (t_blend * 1e-3) / 1e12
         line["stages_ms"] = {"preprocess": t_pre, "binning": t_bin, "blend": t_blend,
                              "note": "stage entry points timed back to back with CUDA events; includes workspace allocs in binning"}
+        traffic = None  # DRAM bytes per launch of the blend kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_blend_traffic.json")
+        if os.path.exists(tpath) and args.n is None:
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line["roofline"] = {"kernel": "blend_kernel", "bound": "fp32_fma", "achieved": blend_tflops, "peak": fp32_peak,
-                            "unit": "TFLOP/s", "frac": blend_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+                            "unit": "TFLOP/s", "frac": blend_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                            "traffic_note": "bytes; the kernel is issue-bound - algorithmic memory side is n_dup*40 + 12*W*H",
                             "peak_source": f"FMA micro-benchmark in this run (gsr_fp32_fma_peak, implies {mhz.value:.0f} MHz)",
                             "evals_warp_granular": warp_evals, "evals_live_pixels": pixel_evals,
                             "gevals_per_s": warp_evals / (t_blend * 1e-3) / 1e9, "flop_per_eval": FLOP_PER_EVAL}
