@@ -1,0 +1,104 @@
+"""Edge cases of the render path on the GPU, each against the C oracle on identical inputs."""
+import numpy as np
+import pytest
+import torch
+
+from gsr_b200 import camera, scenes
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_both(cloud, cam, **kw):
+    from gsr_b200 import render as R
+
+    r = R.Renderer(**kw)
+    img = r.render(R.GaussianModel.from_cloud(cloud), cam).cpu().numpy()
+    ref = c_oracle.render(cloud, cam)
+    return img, ref, r
+
+
+def _one(xyz, log_scale, logit, rgb_dc=(1.0, 0.2, -0.5)):
+    n = len(xyz)
+    z = lambda *s: np.zeros(s, np.float32)
+    rots = z(n, 4); rots[:, 0] = 1
+    f_dc = np.tile(np.array(rgb_dc, np.float32), (n, 1))
+    return scenes.GaussianCloud(np.array(xyz, np.float32), f_dc, z(n, 45), np.full(n, logit, np.float32),
+                                np.full((n, 3), log_scale, np.float32), rots)
+
+
+def test_empty_cloud_renders_black():
+    from gsr_b200 import render as R
+
+    cloud = _one(np.zeros((0, 3)), 0.0, 0.0)
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(70, 50), scenes.front_view(0), 3)
+    img = R.Renderer().render(R.GaussianModel.from_cloud(cloud), cam)
+    assert tuple(img.shape) == (50, 70, 3) and not img.any()
+
+
+@pytest.mark.parametrize("w,h", [(5, 7), (16, 16), (17, 33), (1, 1), (2, 2)])
+def test_images_smaller_than_or_straddling_a_tile(w, h):
+    cloud = scenes.synth_v1(300, 3, scale_factor=2.0)
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(w, h), scenes.front_view(0), 3)
+    img, ref, _ = _render_both(cloud, cam)
+    assert np.abs(img - ref["image"]).max() < 2e-4
+    assert not img[-1].any() and not img[:, -1].any()
+
+
+def test_gaussian_covering_the_whole_frame_takes_the_unculled_large_rect_path():
+    # one opaque splat with a radius of hundreds of pixels (rect far above the 64-tile keep-mask limit) + small ones
+    big = _one([[0.0, 0.0, 0.0]], np.log(1.5), 4.0)
+    small = scenes.synth_v1(500, 9, scale_factor=0.8)
+    cloud = scenes.GaussianCloud(*[np.concatenate([a, b]) for a, b in zip(
+        (big.xyz, big.f_dc, big.f_rest, big.opacity, big.scales, big.rots),
+        (small.xyz, small.f_dc, small.f_rest, small.opacity, small.scales, small.rots))])
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(400, 300), scenes.front_view(0), 3)
+    img, ref, r = _render_both(cloud, cam)
+    assert int(ref["tile_rect"][0, 2] - ref["tile_rect"][0, 0]) * int(ref["tile_rect"][0, 3] - ref["tile_rect"][0, 1]) > 64
+    assert np.abs(img - ref["image"]).max() < 2e-4
+    assert img.max() > 0.5
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3])
+def test_every_sh_degree(degree):
+    cloud = scenes.synth_v1(2000, 77, scale_factor=0.6)
+    intr = scenes.Intrinsics.synthetic(120, 80)
+    cam = camera.camera_for(intr, scenes.orbit_views(1, total=8, first=1)[0], degree)
+    img, ref, _ = _render_both(cloud, cam)
+    assert np.abs(img - ref["image"]).max() < 2e-4
+
+
+def test_invisible_and_degenerate_gaussians_are_harmless():
+    cloud = scenes.synth_v1(400, 5, scale_factor=0.8)
+    cloud.opacity[:50] = -30.0            # opacity ~ 1e-13: never passes alpha > 1/255
+    cloud.xyz[50:100, 2] = -10.0          # behind the camera: culled (z < 0.2)
+    cloud.xyz[100:150, 0] = 500.0         # far off screen
+    cloud.scales[150:160] = -40.0         # vanishing extent: only the 0.3 low-pass remains
+    cloud.rots[160:170] = 0.0             # zero quaternion: normalise() divides by eps, rotation collapses
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(96, 64), scenes.front_view(0), 3)
+    img, ref, r = _render_both(cloud, cam)
+    assert np.isfinite(img).all()
+    assert np.abs(img - ref["image"]).max() < 2e-4
+    assert r.frame_info()["n_visible"] == int((ref["skip"] == 0).sum())
+
+
+def test_workspace_grows_when_max_dup_is_too_small():
+    cloud = scenes.synth_v1(5000, 21, scale_factor=1.0)
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(160, 112), scenes.front_view(0), 3)
+    img, ref, r = _render_both(cloud, cam, dup_factor=0.01)  # first attempt overflows, the renderer redraws
+    assert r.max_dup >= r.frame_info()["n_dup"] > 0.01 * cloud.n
+    assert np.abs(img - ref["image"]).max() < 2e-4
+
+
+def test_render_is_stream_ordered_and_reusable_across_sizes():
+    from gsr_b200 import render as R
+
+    r = R.Renderer()
+    s = torch.cuda.Stream()
+    for (n, w, h) in ((3000, 200, 120), (800, 64, 48), (3000, 200, 120)):
+        cloud = scenes.synth_v1(n, n, scale_factor=0.7)
+        cam = camera.camera_for(scenes.Intrinsics.synthetic(w, h), scenes.front_view(0), 3)
+        with torch.cuda.stream(s):
+            img = r.render(R.GaussianModel.from_cloud(cloud), cam)
+        s.synchronize()
+        assert np.abs(img.cpu().numpy() - c_oracle.render(cloud, cam)["image"]).max() < 2e-4
