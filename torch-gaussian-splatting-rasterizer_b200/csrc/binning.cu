@@ -107,7 +107,11 @@ scan_emit_kernel(int64_t n, const uint32_t *__restrict__ order, const uint32_t *
         const int64_t mine_idx = win - lane;
         unsigned long long v = kScanInclusive;  // before tile 0: an inclusive prefix of zero
         if (mine_idx >= 0) {
-          do { v = ld_volatile_u64(status + mine_idx); } while ((v >> 62) == 0);
+          v = ld_volatile_u64(status + mine_idx);
+          while ((v >> 62) == 0) {  // not published yet: yield the issue slots to working warps
+            __nanosleep(40);
+            v = ld_volatile_u64(status + mine_idx);
+          }
         }
         const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v & kScanInclusive) != 0);
         const int stop = incl ? __ffs(incl) - 1 : 32;  // nearest predecessor that already knows its inclusive prefix

@@ -221,6 +221,10 @@ __device__ __forceinline__ float parabola_max(float q2, float q1, float q0, floa
 __device__ __forceinline__ bool tile_is_empty(const CullGaussian &g, float px0, float py0, float px1, float py1) {
   const float u0 = px0 - g.mx, u1 = px1 - g.mx, v0 = py0 - g.my, v1 = py1 - g.my;
   if (u0 <= 0.0f && u1 >= 0.0f && v0 <= 0.0f && v1 >= 0.0f) return false;  // mean inside: power reaches 0
+  {  // quick accept: the power at the box point nearest to the mean already reaches the limit (most kept tiles)
+    const float cu = fminf(fmaxf(0.0f, u0), u1), cv = fminf(fmaxf(0.0f, v0), v1);
+    if (fmaf(g.A * cu, cu, fmaf(g.C * cv, cv, g.B * cu * cv)) >= g.limit) return false;
+  }
   // edges u = u0 / u1: f(v) = C v^2 + (B u) v + A u^2 ; edges v = v0 / v1: f(u) = A u^2 + (B v) u + C v^2
   float best = parabola_max(g.C, g.B * u0, g.A * u0 * u0, g.kv * u0, v0, v1);
   best = fmaxf(best, parabola_max(g.C, g.B * u1, g.A * u1 * u1, g.kv * u1, v0, v1));

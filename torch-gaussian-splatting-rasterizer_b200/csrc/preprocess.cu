@@ -9,11 +9,6 @@ namespace gsr {
 
 constexpr int kPreThreads = 256;
 
-template <typename T>
-__device__ __forceinline__ T ldg_stream(const T *p) {
-  return __ldg(p);
-}
-
 // Persistent grid-stride kernel, one Gaussian per thread and iteration, three phases:
 //   A  per lane : loads, projection, EWA covariance, radius, tile rect, conic                (rasterize.py:371-420)
 //   B  per warp : exact tile culling of the warp's 32 rects, candidate tiles dealt evenly to the lanes (a lane

@@ -13,13 +13,12 @@
 //
 // n may live on the device (n_dev): grids are sized for the capacity and surplus CTAs retire immediately, so the
 // binning stage never synchronises with the host to learn the number of (Gaussian, tile) pairs.
+#include <stdlib.h>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
 
-constexpr int kSortThreads = 512;
-constexpr int kSortItems = 8;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per CTA
 constexpr int kRadix = 256;
 constexpr int kMaxPasses = 4;
 
@@ -112,45 +111,53 @@ __device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*
 }
 
 // ---- one pass -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads)
+// Big tiles: 1024 threads x ITEMS keys, one CTA per SM, the tile staged in (dynamic) shared memory.  A first version
+// with 4096-key tiles spent most of each pass in the look-back: all CTAs of a wave publish their aggregates at about
+// the same time, so CTA t walks back over t unresolved predecessors - ~300 with two small CTAs per SM, wave after
+// wave.  With ITEMS chosen so that the whole sort is one or two waves of at most 148 CTAs the walk is a handful of
+// 32-wide rounds and the number of look-backs drops 5x.
+constexpr int kBigThreads = 1024;
+constexpr int kBigWarps = kBigThreads / 32;
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kBigThreads, 1)
 onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
                 const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
                 uint32_t *ticket, int shift, uint32_t mask) {
-  __shared__ uint16_t s_hist[kSortThreads / 32][kRadix];  // per-warp digit counts (<= 256), then exclusive over warps (< 4096)
-  __shared__ uint32_t s_excl[kRadix];                     // first tile-local slot of each digit
-  __shared__ uint32_t s_gbase[kRadix];                    // global slot of a digit's first pair minus s_excl
-  __shared__ uint32_t s_keys[kSortTile];
-  __shared__ uint32_t s_vals[kSortTile];
+  constexpr int TILE = kBigThreads * ITEMS;
+  extern __shared__ uint32_t s_dyn[];                      // s_keys[TILE] | s_vals[TILE]
+  uint32_t *s_keys = s_dyn, *s_vals = s_dyn + TILE;
+  __shared__ uint16_t s_hist[kBigWarps][kRadix];           // per-warp digit counts, then exclusive over warps (< TILE <= 65535)
+  __shared__ uint32_t s_excl[kRadix];                      // first tile-local slot of each digit
+  __shared__ uint32_t s_gbase[kRadix];                     // global slot of a digit's first pair minus s_excl
   __shared__ uint2 s_scan[kRadix / 32];
-  __shared__ uint32_t s_part[2][kRadix];
+  __shared__ uint32_t s_part[4][kRadix];
   __shared__ uint32_t s_open[kRadix];
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int k = tid; k < (kSortThreads / 32) * kRadix / 2; k += kSortThreads) reinterpret_cast<uint32_t *>(&s_hist[0][0])[k] = 0;
+  for (int k = tid; k < kBigWarps * kRadix / 2; k += kBigThreads) reinterpret_cast<uint32_t *>(&s_hist[0][0])[k] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
-  const int64_t num_tiles = (n + kSortTile - 1) / kSortTile;
+  const int64_t num_tiles = (n + TILE - 1) / TILE;
   if ((int64_t)tile >= num_tiles) return;
 
-  // ---- load: warp w owns the contiguous run [w*512, (w+1)*512) of the tile, item i of lane l at i*32+l ----
-  const int64_t base = (int64_t)tile * kSortTile + warp * (kSortItems * 32) + lane;
-  uint32_t key[kSortItems], val[kSortItems];
+  // ---- load: warp w owns the contiguous run [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item i of lane l at i*32+l ----
+  const int64_t base = (int64_t)tile * TILE + warp * (ITEMS * 32) + lane;
+  uint32_t key[ITEMS];
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32;
-    const bool live = idx < n;
-    key[i] = live ? __ldg(keys_in + idx) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
-    val[i] = live ? (vals_in ? __ldg(vals_in + idx) : (uint32_t)idx) : 0u;
+    key[i] = idx < n ? __ldg(keys_in + idx) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
   }
 
   // ---- rank inside the warp, in (item, lane) order ----
-  uint16_t rank[kSortItems];  // position among equal digits of this warp, in (item, lane) order
+  uint16_t rank[ITEMS];
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
     const uint32_t peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
@@ -166,8 +173,8 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   // ---- thread d (< 256) owns digit d: counts over warps -> exclusive, tile count ----
   uint32_t count = 0;
   if (tid < kRadix) {
-#pragma unroll
-    for (int w = 0; w < kSortThreads / 32; ++w) {
+#pragma unroll 8
+    for (int w = 0; w < kBigWarps; ++w) {
       const uint32_t c = s_hist[w][tid];
       s_hist[w][tid] = (uint16_t)count;
       count += c;
@@ -175,15 +182,13 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
   const uint2 ex = block_exclusive_scan2(make_uint2(count, tid < kRadix ? __ldg(hist + tid) : 0u), s_scan);
 
-  // ---- decoupled look-back, 32 predecessor tiles per round trip ----
-  // A serial walk costs one L2 latency per tile, and the CTAs of the first wave must walk back over every tile
-  // ahead of them.  Here the two halves of the CTA each fetch 16 predecessors of digit d with independent loads
-  // (coalesced: consecutive threads read consecutive digits of one tile), fold them in order up to the first
-  // inclusive entry, and the halves are combined through shared memory.
+  // ---- decoupled look-back, 32 predecessor tiles per round trip: the four quarters of the CTA each fetch 8
+  //      predecessors of digit d with independent, coalesced loads and fold them in order up to the first inclusive
+  //      entry; the quarters are combined through shared memory ----
   {
-    const int d = tid & (kRadix - 1), half = tid >> 8;
+    const int d = tid & (kRadix - 1), quarter = tid >> 8;
     uint32_t *my_status = status + (size_t)tile * kRadix + d;
-    if (half == 0) {
+    if (quarter == 0) {
       s_excl[d] = ex.x;
       st_volatile_u32(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
       s_open[d] = tile != 0;
@@ -196,8 +201,8 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
       if (__syncthreads_or(open) == 0) break;
       uint32_t part = 0, found = 0;
       if (open) {
-        constexpr int kWin = 16;
-        const int64_t first = prev - (int64_t)half * kWin;
+        constexpr int kWin = 8;
+        const int64_t first = prev - (int64_t)quarter * kWin;
         uint32_t v[kWin];
 #pragma unroll
         for (int i = 0; i < kWin; ++i)
@@ -205,45 +210,51 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
         for (int i = 0; i < kWin; ++i) {
           if (found) break;
-          while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(status + (size_t)(first - i) * kRadix + d);
+          while ((v[i] >> 30) == 0) {  // predecessor not published yet
+            __nanosleep(40);
+            v[i] = ld_volatile_u32(status + (size_t)(first - i) * kRadix + d);
+          }
           part += v[i] & kValueMask;
           found = v[i] >> 31;  // kFlagInclusive
         }
       }
-      s_part[half][d] = part | (found << 31);
+      s_part[quarter][d] = part | (found << 31);
       __syncthreads();
-      if (half == 0 && open) {
-        const uint32_t p0 = s_part[0][d];
-        prefix += p0 & 0x7FFFFFFFu;
-        bool done = p0 >> 31;
-        if (!done) {
-          const uint32_t p1 = s_part[1][d];
-          prefix += p1 & 0x7FFFFFFFu;
-          done = p1 >> 31;
+      if (quarter == 0 && open) {
+        bool done = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!done) {
+            const uint32_t pq = s_part[q][d];
+            prefix += pq & 0x7FFFFFFFu;
+            done = pq >> 31;
+          }
         }
         if (done) s_open[d] = 0;
       }
       prev -= 32;
     }
-    if (half == 0) {
+    if (quarter == 0) {
       if (tile != 0) st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
       s_gbase[d] = ex.y + prefix - ex.x;
     }
   }
   __syncthreads();
 
-  // ---- scatter to the tile-local sorted position, then write runs of equal digits coalesced ----
+  // ---- scatter to the tile-local sorted position (values are fetched only now: they were not needed before) ----
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
     const uint32_t pos = s_excl[d] + s_hist[warp][d] + rank[i];
+    const int64_t idx = base + i * 32;
     s_keys[pos] = key[i];
-    s_vals[pos] = val[i];
+    s_vals[pos] = idx < n ? (vals_in ? __ldg(vals_in + idx) : (uint32_t)idx) : 0u;
   }
   __syncthreads();
-  const int64_t remaining = n - (int64_t)tile * kSortTile;
-  const int valid = remaining < kSortTile ? (int)remaining : kSortTile;
-  for (int j = tid; j < valid; j += kSortThreads) {
+  // ---- runs of equal digits leave coalesced ----
+  const int64_t remaining = n - (int64_t)tile * TILE;
+  const int valid = remaining < TILE ? (int)remaining : TILE;
+  for (int j = tid; j < valid; j += kBigThreads) {
     const uint32_t k = s_keys[j];
     const uint32_t dst = s_gbase[(k >> shift) & mask] + j;
     if (keys_out) keys_out[dst] = k;
@@ -251,8 +262,27 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
 }
 
+// smallest supported tile that keeps the sort within one wave of CTAs (or the largest one)
+static int pick_items(int64_t n, int sms) {
+  static int cap = 0;  // GSR_SORT_MAX_ITEMS=4..24 caps the tile (smaller tiles leave shared memory to other streams)
+  if (cap == 0) {
+    const char *e = getenv("GSR_SORT_MAX_ITEMS");
+    cap = e ? atoi(e) : 24;
+    if (cap < 4 || cap > 24) cap = 24;
+  }
+  const int options[] = {4, 8, 12, 16, 20, 24};
+  int best = 4;
+  for (int it : options) {
+    if (it > cap) break;
+    best = it;
+    if (ceil_div64(n, (int64_t)kBigThreads * it) <= sms) return it;
+  }
+  return best;
+}
+constexpr int kMinSortTile = kBigThreads * 4;  // scratch is sized for the smallest tile
+
 size_t sort_scratch_bytes(int64_t n) {
-  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kSortTile);
+  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kMinSortTile);
   return align_up(sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * tiles * kRadix), 256);
 }
 
@@ -261,7 +291,7 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
     set_error("sort workspace too small or misaligned (%zu < %zu)", bytes, sort_scratch_bytes(n));
     return GSR_ERR_WORKSPACE_TOO_SMALL;
   }
-  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kSortTile);
+  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kMinSortTile);
   uint32_t *p = (uint32_t *)workspace;
   out->hist = p;
   out->tickets = p + kMaxPasses * kRadix;
@@ -282,7 +312,14 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
   const int passes = (bits + 7) / 8;
   const int last_bits = bits - 8 * (passes - 1);
   const uint32_t last_mask = (1u << last_bits) - 1u;
-  const int64_t tiles = ceil_div64(n, kSortTile);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    GSR_CHECK_CUDA(cudaGetDevice(&dev));
+    GSR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int items = pick_items(n, sms);
+  const int64_t tiles = ceil_div64(n, (int64_t)kBigThreads * items);
   const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
   GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
   const uint32_t *hist = ready_hist ? ready_hist : s.hist;  // digit counts may come from the producer of the keys
@@ -300,9 +337,29 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     uint32_t *vout = to_out ? values_out : values_tmp;
     if (p == passes - 1 && skip_final_keys) kout = nullptr;  // caller only wants the permutation
     const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
-    onesweep_kernel<<<(unsigned)tiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, n_dev, hist + p * kRadix,
-                                                                  s.status + p * s.status_stride, s.tickets + p,
-                                                                  begin_bit + 8 * p, mask);
+    const size_t smem = sizeof(uint32_t) * 2 * (size_t)kBigThreads * items;
+#define GSR_SWEEP(IT)                                                                                             \
+  case IT: {                                                                                                      \
+    static bool configured = false;                                                                               \
+    if (!configured) {                                                                                            \
+      GSR_CHECK_CUDA(cudaFuncSetAttribute(onesweep_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                          (int)(sizeof(uint32_t) * 2 * kBigThreads * IT)));                        \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    onesweep_kernel<IT><<<(unsigned)tiles, kBigThreads, smem, stream>>>(kin, vin, kout, vout, n, n_dev,            \
+                                                                        hist + p * kRadix,                        \
+                                                                        s.status + p * s.status_stride,           \
+                                                                        s.tickets + p, begin_bit + 8 * p, mask);   \
+  } break;
+    switch (items) {
+      GSR_SWEEP(4)
+      GSR_SWEEP(8)
+      GSR_SWEEP(12)
+      GSR_SWEEP(16)
+      GSR_SWEEP(20)
+      GSR_SWEEP(24)
+    }
+#undef GSR_SWEEP
     GSR_LAUNCH_CHECK();
     kin = kout;
     vin = vout;
