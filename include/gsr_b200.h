@@ -209,6 +209,12 @@ int gsr_cov2d_fwd(int64_t n, const float *cov3d, const float *cam_means, const g
 /* compute_covering_bbox (:154-198): -> tile rect [n,4] int64. */
 int gsr_bbox_fwd(int64_t n, const float *mean2d, const float *cov2d, int32_t width, int32_t height, int64_t *rect,
                  void *stream);
+/* PLY vertex block -> kernel layout (replaces the host-side column stacking of :353-358, :97-109 and utils.py:21-31).
+ * vertices: device copy of the raw little-endian f32 vertex records, stride_floats floats per vertex;
+ * columns_host59: float index inside a record of x y z, scale_0..2, rot_0..3, opacity, f_dc_0..2, f_rest_0..44.
+ * Outputs: xyz[n,3], log_scales[n,3], rots[n,4], opacity_logit[n], sh_planar[3,16,n]. */
+int gsr_ply_unpack(const float *vertices, int64_t n, int32_t stride_floats, const int32_t *columns_host59, float *xyz,
+                   float *log_scales, float *rots, float *opacity_logit, float *sh_planar, void *stream);
 /* rasterize_gaussian (:255-305): blend ONE Gaussian into the x-major screen[W,H,3] / opacity_buffer[W,H]. */
 int gsr_blend_one(const int64_t *bbox4_host, const float *mean2d_host2, const float *conic_host3,
                   const float *rgb_host3, float opacity, int32_t width, int32_t height, float *screen,

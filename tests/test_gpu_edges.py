@@ -102,3 +102,34 @@ def test_render_is_stream_ordered_and_reusable_across_sizes():
             img = r.render(R.GaussianModel.from_cloud(cloud), cam)
         s.synchronize()
         assert np.abs(img.cpu().numpy() - c_oracle.render(cloud, cam)["image"]).max() < 2e-4
+
+
+def test_ply_device_loader_matches_column_loader(tmp_path):
+    """GaussianModel.from_ply (raw vertex block unpacked on the GPU) == the per-column host route, also for a file
+    whose properties come in another order with extra columns."""
+    import os
+
+    from gsr_b200 import render as R
+    from gsr_b200.ply import GS_PROPERTIES, write_gaussian_ply
+
+    cloud = scenes.synth_v1(1234, 8)
+    ref = R.GaussianModel.from_cloud(cloud)
+    path = str(tmp_path / "a" / "point_cloud.ply")
+    write_gaussian_ply(path, cloud.ply_table())
+    m = R.GaussianModel.from_ply(path)
+    for a, b in ((m.xyz, ref.xyz), (m.log_scales, ref.log_scales), (m.rots, ref.rots), (m.opacity, ref.opacity), (m.sh, ref.sh)):
+        assert torch.equal(a, b)
+    assert m.sh.stride() == (1, 1234, 16 * 1234)  # planar [3,16,N] storage
+    # permuted property order + two foreign float columns
+    rng = np.random.default_rng(0)
+    names = list(GS_PROPERTIES) + ["extra_a", "extra_b"]
+    perm = rng.permutation(len(names))
+    table = np.concatenate([cloud.ply_table(), rng.normal(size=(cloud.n, 2)).astype(np.float32)], axis=1)[:, perm]
+    path2 = str(tmp_path / "b.ply")
+    head = ["ply", "format binary_little_endian 1.0", f"element vertex {cloud.n}"]
+    head += [f"property float {names[j]}" for j in perm] + ["end_header", ""]
+    with open(path2, "wb") as fh:
+        fh.write("\n".join(head).encode("ascii")); fh.write(np.ascontiguousarray(table, dtype="<f4").tobytes())
+    m2 = R.GaussianModel.from_ply(path2)
+    for a, b in ((m2.xyz, ref.xyz), (m2.rots, ref.rots), (m2.opacity, ref.opacity), (m2.sh, ref.sh)):
+        assert torch.equal(a, b)

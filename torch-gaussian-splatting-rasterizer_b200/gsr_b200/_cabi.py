@@ -77,6 +77,8 @@ PROTOTYPES = {
     "gsr_affine_fwd": [c_int64, c_void_p, c_int64, c_int64, POINTER(c_float), c_int32, c_void_p, c_void_p],
     "gsr_cov2d_fwd": [c_int64, c_void_p, c_void_p, POINTER(CameraStruct), c_void_p, c_void_p],
     "gsr_bbox_fwd": [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
+    "gsr_ply_unpack": [c_void_p, c_int64, c_int32, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_void_p],
     "gsr_blend_one": [POINTER(c_int64), POINTER(c_float), POINTER(c_float), POINTER(c_float), c_float, c_int32,
                       c_int32, c_void_p, c_void_p, c_void_p],
 }

@@ -71,6 +71,28 @@ class GaussianModel:
         return GaussianModel.from_tensors(torch.from_numpy(cloud.xyz), torch.from_numpy(cloud.scales),
                                           torch.from_numpy(cloud.rots), torch.from_numpy(cloud.opacity), sh, device)
 
+    @staticmethod
+    def from_ply(path: str, device="cuda") -> "GaussianModel":
+        """3DGS PLY file -> HBM in the kernel layout: the raw vertex block is uploaded once (pinned staging) and
+        de-interleaved on the GPU by ``gsr_ply_unpack``; no per-column work on the host."""
+        from .ply import read_vertex_block
+
+        _cabi.require_cuda()
+        block, names = read_vertex_block(path)  # [n, P] float32 view of the file's vertex records
+        want = (["x", "y", "z", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3", "opacity",
+                 "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{j}" for j in range(45)])
+        missing = [w for w in want if w not in names]
+        if missing:
+            raise ValueError(f"{path}: missing 3DGS properties {missing[:4]}")
+        cols = (ctypes.c_int32 * 59)(*[names.index(w) for w in want])
+        n, stride = block.shape
+        raw = torch.from_numpy(block).pin_memory().to(device, non_blocking=True)
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        xyz, ls, rot, op, planar = f(n, 3), f(n, 3), f(n, 4), f(n), f(3, 16, n)
+        _cabi.call("gsr_ply_unpack", _cabi.ptr(raw), n, stride, cols, _cabi.ptr(xyz), _cabi.ptr(ls), _cabi.ptr(rot),
+                   _cabi.ptr(op), _cabi.ptr(planar), _cabi.stream_handle())
+        return GaussianModel(xyz, ls, rot, op, planar.permute(2, 1, 0))
+
     def c_struct(self) -> _cabi.Gaussians:
         g = _cabi.Gaussians()
         g.n = self.n

@@ -146,17 +146,9 @@ def rasterize_gaussian(gaussian_index: int, bboxes: torch.Tensor, screen: torch.
 # ----------------------------------------------------------------------------------------------
 def load_model(trained_model_path: str, device: str = "cuda") -> GaussianModel:
     """``<path>/point_cloud/iteration_30000/point_cloud.ply`` (reference :353) straight into the kernel layout."""
-    from gsr_b200.ply import PlyData
-
     ply_path = os.path.join(trained_model_path, "point_cloud/iteration_30000/point_cloud.ply")
     logger.info("Fetching trained model from: %s", ply_path)
-    plydata = PlyData.read(ply_path)
-    el = plydata.elements[0]
-    stack = lambda names: torch.from_numpy(np.stack([el[k] for k in names], axis=1).astype(np.float32))
-    return GaussianModel.from_tensors(stack(["x", "y", "z"]), stack(["scale_0", "scale_1", "scale_2"]),
-                                      stack([f"rot_{i}" for i in range(4)]),
-                                      torch.from_numpy(np.asarray(el["opacity"], dtype=np.float32)),
-                                      read_color_components(plydata), device=device)
+    return GaussianModel.from_ply(ply_path, device=device)
 
 
 def camera_from_scene(scene, cam_info, width: int, height: int, degree: int = 3) -> "_camera.CameraStruct":
