@@ -124,6 +124,7 @@ class Renderer:
         self._ws_key = None
         self.max_dup = 0
         self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)  # gsr_frame_info (32 bytes)
+        self.adaptive_capacity = True
         self.frame_serial = 0  # bumped by every frame: backward must replay the workspace of ITS forward
 
     # -- workspace ---------------------------------------------------------------------------
@@ -167,6 +168,13 @@ class Renderer:
                 continue
             if info["status"] != _cabi.GSR_OK:
                 raise _cabi.GsrError(info["status"], "frame failed")
+            # Tighten the pair capacity to what frames of this scene need (+30 %): grids and look-back tables of the
+            # pair sort are sized by capacity, so a loose one costs idle CTAs and memset bytes.  The allocation
+            # stays; an overflow on a later view is detected on the device and triggers one redraw.
+            tight = max(int(1.3 * info["n_dup"]) + 4096, 1 << 16)
+            if self.adaptive_capacity and tight < self.max_dup:
+                self.max_dup = tight
+                self._ws_key = (model.n, W, H, tight)
             return out
 
     def frame_info(self) -> Dict[str, int]:
