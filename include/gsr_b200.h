@@ -114,17 +114,17 @@ int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t 
  *  tiles_touched[n]  u32: bit 31 = the reference's loop would blend this Gaussian (not culled / skipped / off
  *                    screen, :441); bits 0..30 = number of tiles of its rect in which at least one pixel can pass
  *                    alpha > 1/255 (exact tile culling, see gsr_math.cuh) - the image is unchanged by the culling
- *  rect[n,4]         u16 tile rect (x0,y0,x1,y1), clipped to the tile grid and to [row_begin,row_end)
- *  tile_mask[n,2]    u32 x2: keep mask of the rect's tiles, row-major, for rects of <= 64 tiles (larger: all kept)
+ *  tile_span[n,4]    u32: x0 | y0 << 16, x1 | y1 << 16 (tile rect clipped to the tile grid and to
+ *                    [row_begin,row_end)), then the 64-bit keep mask of the rect's tiles, row-major, for rects of
+ *                    <= 64 tiles (larger rects keep every tile).  16-byte aligned: the binning stage gathers it
+ *                    with one load per Gaussian
  *  rec[n,12]         blend record (written for visible Gaussians only)
  * optional debug outputs (may be NULL): cov3d[n,9], cov2d[n,4] (after cull zeroing), tile_rect_raw[n,4] i32
  * (the reference's compute_covering_bbox result), mean2d_all[n,2]; depth_hist[4*256] u32 receives the 8-bit digit
- * histograms of depth_key (input of gsr_bin's one-sweep sort); tile_count[tiles] u32 the list length of every tile and
- * info_dev->n_visible the number of Gaussians the reference's loop blends (inputs of gsr_bin's bucket path). */
+ * histograms of the depth keys of the Gaussians the reference's loop blends (input of gsr_bin's one-sweep sort). */
 int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t tile_row_begin, int32_t tile_row_end,
-                       uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, uint32_t *tile_mask, float *rec,
-                       float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist,
-                       uint32_t *tile_count, gsr_frame_info *info_dev, void *stream);
+                       uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span, float *rec, float *cov3d,
+                       float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist, void *stream);
 
 /* spherical_harmonics.sh_to_rgb (spherical_harmonics.py:27-73): rgb[n,3] contiguous. */
 int gsr_sh_fwd(int64_t n, const float *xyz, int64_t xyz_sn, int64_t xyz_sc, const float *sh, int64_t sh_sn,
@@ -140,23 +140,21 @@ int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t 
 
 /* Binning: global stable depth sort (:424-425, ties by Gaussian index), duplication into (tile, Gaussian) pairs
  * in depth order, stable sort by tile, tile range extraction.  Equivalent to sorting 64-bit (tile|depth) keys.
- *  depth_hist[4*256]  u32 digit histograms of depth_key as written by gsr_preprocess_fwd (in, may be NULL:
- *                     they are then counted here)
- *  tile_count[tiles]  u32 list length of every tile as counted by gsr_preprocess_fwd (in, may be NULL)
- *  depth_order[n]     u32 Gaussian ids in ascending depth                 (out, may be NULL - see below)
- *  blend_rank[n]      u32 rank of each visible Gaussian among the Gaussians the reference's loop would
- *                     blend, in blend order (out, may be NULL; feeds progressive renders)
+ *  depth_hist[4*256]  u32 digit histograms of the blended Gaussians' depth keys as written by gsr_preprocess_fwd
+ *                     (in, may be NULL: they are then counted here)
+ *  tile_span[n,4]     u32 tile rect + keep mask as written by gsr_preprocess_fwd (in)
+ *  depth_order[n]     u32 ids of the Gaussians the reference's loop blends, in ascending depth; only the first
+ *                     info_dev->n_visible entries are written            (out, may be NULL: kept in the workspace)
+ *  blend_rank[n]      u32 rank of each blended Gaussian in that order (out, may be NULL; feeds progressive
+ *                     renders; entries of the other Gaussians are left untouched)
  *  tile_gids[max_dup] u32 Gaussian ids grouped by tile, depth-sorted      (out)
- *  tile_ranges[tiles,2] u32 [begin,end) into tile_gids                    (out)
- *  info_dev->n_dup / status are filled, n_visible too on the ordered path (info_dev may be NULL).
- * Two routes to the SAME lists: with depth_order == NULL ("bucket path") pairs are dropped into their tile's segment
- * through atomic cursors and each segment is sorted on chip by (depth key, Gaussian id); with depth_order given
- * ("ordered path", needed for blend_rank) the global sort + scan + tile sort described above runs. */
+ *  tile_ranges[tiles,2] u32 [begin,end) into tile_gids; (0,0) for tiles without pairs (out)
+ *  info_dev->n_visible / n_dup / status are filled (info_dev may be NULL). */
 int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
 int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
-            const uint16_t *rect, const uint32_t *tile_mask, const uint32_t *tile_count, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
-            uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
-            void *workspace, size_t workspace_bytes, void *stream);
+            const uint32_t *tile_span, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+            uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
+            size_t workspace_bytes, void *stream);
 
 /* Per-16x16-tile front-to-back alpha blend (:255-305, :436-446).  Pixels x >= W-1 or y >= H-1 are written
  * as zero (the reference never writes them).  When blend_rank is given, only Gaussians with

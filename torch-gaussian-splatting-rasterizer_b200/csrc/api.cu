@@ -17,7 +17,7 @@ void set_error(const char *fmt, ...) {
 }
 
 struct FrameLayout {
-  size_t depth_key, depth_hist, tile_count, tiles_touched, rect, tile_mask, rec, order, blend_rank, tile_gids, tile_ranges, bin, total;
+  size_t depth_key, depth_hist, tiles_touched, tile_span, rec, order, blend_rank, tile_gids, tile_ranges, bin, total;
   size_t bin_bytes;
 };
 
@@ -32,10 +32,8 @@ static int frame_layout(int64_t n, int width, int height, int64_t max_dup, Frame
   const TileGrid tg = make_grid(width, height);
   L->depth_key = take(4 * n1);
   L->depth_hist = take(4 * 1024);
-  L->tile_count = take(4 * (size_t)tg.tiles_x * tg.tiles_y);
   L->tiles_touched = take(4 * n1);
-  L->rect = take(8 * n1);
-  L->tile_mask = take(8 * n1);
+  L->tile_span = take(16 * n1);
   L->rec = take(sizeof(float) * GSR_REC_FLOATS * n1);
   L->order = take(4 * n1);
   L->blend_rank = take(4 * n1);
@@ -143,26 +141,17 @@ extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int
   if (tile_row_end < 0 || tile_row_end > tg.tiles_y) tile_row_end = tg.tiles_y;
   char *ws = (char *)workspace;
   uint32_t *depth_key = (uint32_t *)(ws + L.depth_key), *tiles_touched = (uint32_t *)(ws + L.tiles_touched);
-  uint16_t *rect = (uint16_t *)(ws + L.rect);
-  uint32_t *tile_mask = (uint32_t *)(ws + L.tile_mask);
+  uint32_t *tile_span = (uint32_t *)(ws + L.tile_span);
   float *rec = (float *)(ws + L.rec);
   uint32_t *order = (uint32_t *)(ws + L.order), *blend_rank = (uint32_t *)(ws + L.blend_rank);
   uint32_t *tile_gids = (uint32_t *)(ws + L.tile_gids), *tile_ranges = (uint32_t *)(ws + L.tile_ranges);
   const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
   if (info_dev) GSR_CHECK_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(gsr_frame_info), stream));
   uint32_t *depth_hist = (uint32_t *)(ws + L.depth_hist);
-  // gsr_bin has two routes to the same tile lists.  The ordered path (global one-sweep sort, scan, tile sort) is the
-  // default; the bucket path (atomic cursors + on-chip bitonic sort per tile, GSR_BIN_BUCKET=1) builds identical
-  // lists with no global sort but is currently slower on B200 (profiles/r01_notes.md) - kept for round 2.
-  static const bool use_bucket = getenv("GSR_BIN_BUCKET") && atoi(getenv("GSR_BIN_BUCKET")) != 0;
-  const bool ordered = windowed || !use_bucket;
-  uint32_t *tile_count = (uint32_t *)(ws + L.tile_count);
-  rc = gsr_preprocess_fwd(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, rect, tile_mask, rec, nullptr,
-                          nullptr, nullptr, nullptr, ordered ? depth_hist : nullptr, ordered ? nullptr : tile_count,
-                          ordered ? nullptr : info_dev, stream);
+  rc = gsr_preprocess_fwd(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span, rec, nullptr, nullptr,
+                          nullptr, nullptr, depth_hist, stream);
   if (rc) return rc;
-  rc = gsr_bin(g->n, depth_key, ordered ? depth_hist : nullptr, tiles_touched, rect, tile_mask,
-               ordered ? nullptr : tile_count, cam->width, cam->height, max_dup, ordered ? order : nullptr,
+  rc = gsr_bin(g->n, depth_key, depth_hist, tiles_touched, tile_span, cam->width, cam->height, max_dup, order,
                windowed ? blend_rank : nullptr, tile_gids, tile_ranges, info_dev, ws + L.bin, L.bin_bytes, stream);
   if (rc) return rc;
   return gsr_blend_fwd(rec, tile_gids, tile_ranges, cam->width, cam->height, tile_row_begin, tile_row_end,

@@ -19,10 +19,9 @@ constexpr int kPreThreads = 256;
 __global__ void __launch_bounds__(kPreThreads, 2)
 preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
                   uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
-                  ushort4 *__restrict__ rect_out, uint2 *__restrict__ tile_mask, float4 *__restrict__ rec,
+                  uint4 *__restrict__ span_out, float4 *__restrict__ rec,
                   float *__restrict__ cov3d_out, float *__restrict__ cov2d_out, int *__restrict__ rect_raw_out,
-                  float *__restrict__ mean2d_out, uint32_t *__restrict__ depth_hist, uint32_t *__restrict__ tile_count,
-                  gsr_frame_info *__restrict__ info) {
+                  float *__restrict__ mean2d_out, uint32_t *__restrict__ depth_hist) {
   constexpr int kWarps = kPreThreads / 32;
   __shared__ uint32_t s_hist[4][256];
   __shared__ CullGaussian s_cg[kWarps][32];
@@ -168,35 +167,16 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
       tiles = (uint32_t)(__popc(mask_lo) + __popc(mask_hi));
     }
 
-    // list lengths of the tiles (fire-and-forget REDs) and the number of Gaussians the reference's loop blends
-    if (tile_count && tiles) {
-      if (area <= kCullMaxTiles) {
-        unsigned long long m = ((unsigned long long)mask_hi << 32) | mask_lo;
-        if (area < 64) m &= (1ull << area) - 1ull;
-        while (m) {
-          const int bit = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const int row = (bit * s_rect[warp][lane].w) >> 16, col = bit - row * w;
-          atomicAdd(tile_count + (y0 + row) * tg.tiles_x + x0 + col, 1u);
-        }
-      } else {
-        for (int ty = y0; ty < y1; ++ty)
-          for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_count + ty * tg.tiles_x + tx, 1u);
-      }
-    }
-    if (info) {
-      const uint32_t nb = __popc(__ballot_sync(0xFFFFFFFFu, blendable));
-      if (lane == 0 && nb) atomicAdd(&info->n_visible, nb);
-    }
     __syncwarp();  // shared arrays are rewritten by the next iteration
 
     const uint32_t key = float_to_key(camp[2]);
     if (active) {
       depth_key[i] = key;
       tiles_touched[i] = tiles | (blendable ? 0x80000000u : 0u);  // bit 31: counted by the reference's loop (:441)
-      rect_out[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-      if (blendable) tile_mask[i] = make_uint2(mask_lo, mask_hi);
-      if (depth_hist) {
+      // tile span: rect (x0 | y0 << 16, x1 | y1 << 16) + keep mask, one 16-byte word - the only thing the binning
+      // stage gathers per Gaussian
+      span_out[i] = make_uint4((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16), mask_lo, mask_hi);
+      if (depth_hist && blendable) {  // only the Gaussians the reference's loop blends are depth-sorted
 #pragma unroll
         for (int q = 0; q < 4; ++q) atomicAdd(&s_hist[q][(key >> (8 * q)) & 255u], 1u);
       }
@@ -322,28 +302,24 @@ static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n
 using namespace gsr;
 
 extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t row_begin, int32_t row_end,
-                                  uint32_t *depth_key, uint32_t *tiles_touched, uint16_t *rect, uint32_t *tile_mask,
-                                  float *rec, float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all,
-                                  uint32_t *depth_hist, uint32_t *tile_count, gsr_frame_info *info_dev, void *stream) {
+                                  uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span, float *rec,
+                                  float *cov3d, float *cov2d, int32_t *tile_rect_raw, float *mean2d_all,
+                                  uint32_t *depth_hist, void *stream) {
   GSR_REQUIRE(g && cam, "null gaussians/camera");
   GSR_REQUIRE(g->n >= 0 && g->n < (1ll << 31), "n out of range");
   GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
   GSR_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 65535 * GSR_TILE && cam->height <= 65535 * GSR_TILE,
               "image size out of range");
-  GSR_REQUIRE(depth_key && tiles_touched && rect && tile_mask && rec, "null output");
-  GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)rect & 7) == 0, "rec must be 16-byte and rect 8-byte aligned");
+  GSR_REQUIRE(depth_key && tiles_touched && tile_span && rec, "null output");
+  GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)tile_span & 15) == 0, "rec and tile_span must be 16-byte aligned");
   if (depth_hist) GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * 1024, (cudaStream_t)stream));
-  if (tile_count) {
-    const TileGrid tg = make_grid(cam->width, cam->height);
-    GSR_CHECK_CUDA(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (size_t)tg.tiles_x * tg.tiles_y, (cudaStream_t)stream));
-  }
   if (g->n == 0) return GSR_OK;
   unsigned blocks = blocks_for(g->n, kPreThreads);
   const unsigned resident = 148 * 4;  // persistent: a few CTAs per SM, each loops over its share
   if (blocks > resident) blocks = resident;
-  preprocess_kernel<<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(
-      *g, *cam, row_begin, row_end, depth_key, tiles_touched, (ushort4 *)rect, (uint2 *)tile_mask, (float4 *)rec, cov3d,
-      cov2d, tile_rect_raw, mean2d_all, depth_hist, tile_count, info_dev);
+  preprocess_kernel<<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(*g, *cam, row_begin, row_end, depth_key, tiles_touched,
+                                                                     (uint4 *)tile_span, (float4 *)rec, cov3d, cov2d,
+                                                                     tile_rect_raw, mean2d_all, depth_hist);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

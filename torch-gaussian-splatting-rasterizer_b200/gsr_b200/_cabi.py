@@ -53,16 +53,15 @@ PROTOTYPES = {
                        c_void_p, c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p],
     "gsr_render_host": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, POINTER(FrameInfo)],
     "gsr_preprocess_fwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                           c_void_p],
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gsr_sh_fwd": [c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, POINTER(c_float), c_int32,
                    c_void_p, c_void_p],
     "gsr_sort_workspace_bytes": [c_int64, POINTER(c_size_t)],
     "gsr_sort_pairs": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32,
                        c_void_p, c_size_t, c_void_p],
     "gsr_bin_workspace_bytes": [c_int64, c_int32, c_int32, c_int64, POINTER(c_size_t)],
-    "gsr_bin": [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p,
-                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "gsr_bin": [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "gsr_blend_fwd": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_uint32, c_uint32,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gsr_blend_bwd": [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,

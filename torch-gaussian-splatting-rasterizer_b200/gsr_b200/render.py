@@ -319,20 +319,15 @@ def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: O
 # ----------------------------------------------------------------------------------------------
 # stage-level wrappers (tests and profiling drive the stages one by one)
 # ----------------------------------------------------------------------------------------------
-def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, tile_rows=None,
-               count_tiles: bool = False) -> Dict[str, torch.Tensor]:
+def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, tile_rows=None) -> Dict[str, torch.Tensor]:
     _cabi.require_cuda()
     n, dev = model.n, model.device
     rb, re = (0, 1 << 30) if tile_rows is None else tile_rows
     out = dict(depth_key=torch.empty(n, dtype=torch.int32, device=dev),
                tiles_touched=torch.empty(n, dtype=torch.int32, device=dev),
-               rect=torch.empty((n, 4), dtype=torch.int16, device=dev),
-               tile_mask=torch.zeros((n, 2), dtype=torch.int32, device=dev),
+               tile_span=torch.zeros((n, 4), dtype=torch.int32, device=dev),
                rec=torch.zeros((n, _cabi.REC_FLOATS), dtype=torch.float32, device=dev),
-               depth_hist=torch.empty(1024, dtype=torch.int32, device=dev),
-               info=torch.zeros(8, dtype=torch.int32, device=dev))
-    if count_tiles:  # per-tile list lengths for gsr_bin's bucket path
-        out["tile_count"] = torch.empty(((cam.width + 15) // 16) * ((cam.height + 15) // 16), dtype=torch.int32, device=dev)
+               depth_hist=torch.empty(1024, dtype=torch.int32, device=dev))
     if debug:
         out.update(cov3d=torch.empty((n, 3, 3), dtype=torch.float32, device=dev),
                    cov2d=torch.empty((n, 2, 2), dtype=torch.float32, device=dev),
@@ -340,10 +335,12 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
                    mean2d=torch.empty((n, 2), dtype=torch.float32, device=dev))
     g = model.c_struct()
     _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), rb, re, _cabi.ptr(out["depth_key"]),
-               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["rect"]), _cabi.ptr(out["tile_mask"]), _cabi.ptr(out["rec"]),
+               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["tile_span"]), _cabi.ptr(out["rec"]),
                _cabi.ptr(out.get("cov3d")), _cabi.ptr(out.get("cov2d")), _cabi.ptr(out.get("tile_rect")),
-               _cabi.ptr(out.get("mean2d")), _cabi.ptr(out["depth_hist"]), _cabi.ptr(out.get("tile_count")),
-               _cabi.ptr(out["info"]), _cabi.stream_handle())
+               _cabi.ptr(out.get("mean2d")), _cabi.ptr(out["depth_hist"]), _cabi.stream_handle())
+    # views of the span: the clipped (and culling-shrunk) tile rect as u16 x0,y0,x1,y1 and the 64-bit keep mask
+    out["rect"] = out["tile_span"].view(torch.int16)[:, :4]
+    out["tile_mask"] = out["tile_span"][:, 2:4]
     return out
 
 
@@ -360,10 +357,8 @@ def sort_pairs(keys: torch.Tensor, values: Optional[torch.Tensor], begin_bit: in
     return ko, vo
 
 
-def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: int,
-              ordered: bool = True) -> Dict[str, torch.Tensor]:
-    """Tile lists from the preprocess outputs.  ``ordered=True``: gsr_bin's ordered path (also returns the global
-    depth order and blend ranks); ``False``: the bucket path every un-windowed frame takes."""
+def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: int) -> Dict[str, torch.Tensor]:
+    """Tile lists from the preprocess outputs, plus the global depth order and the blend ranks."""
     _cabi.require_cuda()
     dev = pre["depth_key"].device
     n = pre["depth_key"].numel()
@@ -376,15 +371,10 @@ def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: in
                tile_gids=torch.empty(max_dup, dtype=torch.int32, device=dev),
                tile_ranges=torch.empty((tiles, 2), dtype=torch.int32, device=dev),
                info=torch.zeros(8, dtype=torch.int32, device=dev))
-    if not ordered:
-        out["info"].copy_(pre["info"])  # n_visible was counted by the preprocess kernel
     _cabi.call("gsr_bin", n, _cabi.ptr(pre["depth_key"]), _cabi.ptr(pre.get("depth_hist")),
-               _cabi.ptr(pre["tiles_touched"]), _cabi.ptr(pre["rect"]), _cabi.ptr(pre["tile_mask"]),
-               _cabi.ptr(pre.get("tile_count")) if not ordered else None,
-               width, height, max_dup, _cabi.ptr(out["order"]) if ordered else None,
-               _cabi.ptr(out["blend_rank"]) if ordered else None,
-               _cabi.ptr(out["tile_gids"]), _cabi.ptr(out["tile_ranges"]), _cabi.ptr(out["info"]), _cabi.ptr(ws),
-               ws.numel(), _cabi.stream_handle())
+               _cabi.ptr(pre["tiles_touched"]), _cabi.ptr(pre["tile_span"]), width, height, max_dup,
+               _cabi.ptr(out["order"]), _cabi.ptr(out["blend_rank"]), _cabi.ptr(out["tile_gids"]),
+               _cabi.ptr(out["tile_ranges"]), _cabi.ptr(out["info"]), _cabi.ptr(ws), ws.numel(), _cabi.stream_handle())
     out["_ws"] = ws
     return out
 
