@@ -16,6 +16,7 @@ constexpr int kPreThreads = 256;
 //   C  per lane : SH colour + blend record, only for Gaussians that keep at least one tile
 // It also accumulates the four 8-bit digit histograms of the depth keys (global digit counts of the one-sweep
 // sort) in shared memory and flushes them once per CTA.
+template <int DEGREE>
 __global__ void __launch_bounds__(kPreThreads, 2)
 preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
                   uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
@@ -33,8 +34,8 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
     for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&s_hist[0][0])[k] = 0;
     __syncthreads();
   }
-  const int degree = cam.sh_degree;
-  const int ncoef = (degree + 1) * (degree + 1);
+  constexpr int degree = DEGREE;
+  constexpr int ncoef = (degree + 1) * (degree + 1);
   const TileGrid tg = make_grid(cam.width, cam.height);
   const int64_t stride = (int64_t)gridDim.x * kPreThreads;
   for (int64_t base = (int64_t)blockIdx.x * kPreThreads + warp * 32; base < g.n; base += stride) {
@@ -50,12 +51,16 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
 #pragma unroll
     for (int c = 0; c < 4; ++c) rot[c] = __ldg(g.rots + i * g.rot_sn + c * g.rot_sc);
     const float op_logit = __ldg(g.opacity_logit + i * g.opacity_sn);
-    float sh[3][16];
-    const float *shp = g.sh + i * g.sh_sn;
+    float sh[3][ncoef];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c) {
+      const float *shp = g.sh + i * g.sh_sn + c * g.sh_sc;  // walk the coefficients by pointer: one add per load
 #pragma unroll
-      for (int k = 0; k < 16; ++k) sh[c][k] = (k < ncoef) ? __ldg(shp + k * g.sh_sk + c * g.sh_sc) : 0.0f;
+      for (int k = 0; k < ncoef; ++k) {
+        sh[c][k] = __ldg(shp);
+        shp += g.sh_sk;
+      }
+    }
 
     // ---- A: geometry, rasterize.py:371-420 ----
     float camp[3], clip[4];
@@ -66,8 +71,8 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
     const bool culled = camp[2] < 0.2f;  // :377
     if (culled) clip[0] = clip[1] = clip[3] = 0.0f;
     const float pw = frcp(fadd(clip[3], 0.0000001f));  // :381
-    const float mx = fdiv(fsub(fmul(fadd(fmul(clip[0], pw), 1.0f), (float)cam.width), 1.0f), 2.0f);   // :391
-    const float my = fdiv(fsub(fmul(fadd(fmul(clip[1], pw), 1.0f), (float)cam.height), 1.0f), 2.0f);
+    const float mx = fmul(fsub(fmul(fadd(fmul(clip[0], pw), 1.0f), (float)cam.width), 1.0f), 0.5f);   // :391 (/ 2)
+    const float my = fmul(fsub(fmul(fadd(fmul(clip[1], pw), 1.0f), (float)cam.height), 1.0f), 0.5f);
     float S[9], c2[4];
     covariance3d(ls, rot, S);
     covariance2d(S, camp, cam, c2);
@@ -204,7 +209,7 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
       view_direction(p, cam.cam_center, dx, dy, dz);
       float rgb[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) rgb[c] = sh_channel(dx, dy, dz, degree, [&](int k) { return sh[c][k]; });
+      for (int c = 0; c < 3; ++c) rgb[c] = sh_channel(dx, dy, dz, degree, [&](int k) { return sh[c][k < ncoef ? k : 0]; });
       rec[i * 3 + 0] = make_float4(mx, my, A, C);
       rec[i * 3 + 1] = make_float4(B, thr, opacity, rgb[0]);
       rec[i * 3 + 2] = make_float4(rgb[1], rgb[2], opacity > 0.0f ? log2f(opacity) : -1e30f, radius);
@@ -317,9 +322,18 @@ extern "C" int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam,
   unsigned blocks = blocks_for(g->n, kPreThreads);
   const unsigned resident = 148 * 4;  // persistent: a few CTAs per SM, each loops over its share
   if (blocks > resident) blocks = resident;
-  preprocess_kernel<<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(*g, *cam, row_begin, row_end, depth_key, tiles_touched,
-                                                                     (uint4 *)tile_span, (float4 *)rec, cov3d, cov2d,
-                                                                     tile_rect_raw, mean2d_all, depth_hist);
+#define GSR_PRE(D)                                                                                                \
+  preprocess_kernel<D><<<blocks, kPreThreads, 0, (cudaStream_t)stream>>>(*g, *cam, row_begin, row_end, depth_key,     \
+                                                                        tiles_touched, (uint4 *)tile_span,           \
+                                                                        (float4 *)rec, cov3d, cov2d, tile_rect_raw,  \
+                                                                        mean2d_all, depth_hist)
+  switch (cam->sh_degree) {  // the SH degree fixes the number of loads and the colour polynomial at compile time
+    case 0: GSR_PRE(0); break;
+    case 1: GSR_PRE(1); break;
+    case 2: GSR_PRE(2); break;
+    default: GSR_PRE(3); break;
+  }
+#undef GSR_PRE
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }
