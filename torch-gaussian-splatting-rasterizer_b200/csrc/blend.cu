@@ -90,12 +90,14 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   auto issue = [&](int buf) {
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
+      float *dst = &s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS];
       if (gnext[r] != 0xFFFFFFFFu) {
         const float4 *src = rec + (size_t)gnext[r] * 3;
-        float *dst = &s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS];
         cp_async16(dst, src);
         cp_async16(dst + 4, src + 1);
         cp_async16(dst + 8, src + 2);
+      } else {
+        dst[5] = __int_as_float(0x7f800000);  // slot past the end of the list: thr = +inf, no pixel passes the test
       }
     }
     cp_async_commit();
@@ -130,43 +132,48 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     const int count = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
     if (__any_sync(0xFFFFFFFFu, live > 0)) {  // warp-uniform: finished lanes idle along (their pixels are parked)
       const float *base = s_rec[buf];
-#pragma unroll 2
-      for (int j = 0; j < count; ++j) {
-        const float4 q = *reinterpret_cast<const float4 *>(base + j * GSR_REC_FLOATS);      // mx my A C
-        const float2 w = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 4);  // B thr
-        if (COUNT) {
-          ++my_iters;
-          my_evals += live;
-        }
-        const float dx = fsub(q.x, fx);
-        const float adx2 = fmul(q.z, fmul(dx, dx));
-        const float bdx = fmul(w.x, dx);
-        float power[PX];
-        bool any = false;
+      // The list is walked four records at a time with no bound check inside the group: slots past the end of the
+      // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
+      const int count4 = (count + 3) & ~3;
+      for (int j = 0; j < count4; j += 4) {
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-          const float dy = fsub(q.y, fy[k]);
-          // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
-          power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
-          any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
-        }
-        if (any) {
-          const float2 orr = *reinterpret_cast<const float2 *>(base + j * GSR_REC_FLOATS + 6);  // opacity r
-          const float4 gbl = *reinterpret_cast<const float4 *>(base + j * GSR_REC_FLOATS + 8);  // g b log2(opacity) .
+        for (int u = 0; u < 4; ++u) {
+          const float4 q = *reinterpret_cast<const float4 *>(base + (j + u) * GSR_REC_FLOATS);      // mx my A C
+          const float2 w = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 4);  // B thr
+          if (COUNT && j + u < count) {
+            ++my_iters;
+            my_evals += live;
+          }
+          const float dx = fsub(q.x, fx);
+          const float adx2 = fmul(q.z, fmul(dx, dx));
+          const float bdx = fmul(w.x, dx);
+          float power[PX];
+          bool any = false;
 #pragma unroll
           for (int k = 0; k < PX; ++k) {
-            if (power[k] >= w.y) {
-              float alpha;
-              if (blend_alpha(power[k], orr.x, gbl.z, alpha)) {
-                const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
-                C0[k] = fmaf(wgt, orr.y, C0[k]);
-                C1[k] = fmaf(wgt, gbl.x, C1[k]);
-                C2[k] = fmaf(wgt, gbl.y, C2[k]);
-                T[k] = fmaf(-alpha, T[k], T[k]);
-                last[k] = (uint32_t)b * kBatch + j + 1;
-                if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
-                  fy[k] = kParkedY;
-                  --live;
+            const float dy = fsub(q.y, fy[k]);
+            // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
+            power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
+            any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
+          }
+          if (any) {
+            const float2 orr = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 6);  // opacity r
+            const float4 gbl = *reinterpret_cast<const float4 *>(base + (j + u) * GSR_REC_FLOATS + 8);  // g b log2(opacity) .
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+              if (power[k] >= w.y) {
+                float alpha;
+                if (blend_alpha(power[k], orr.x, gbl.z, alpha)) {
+                  const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
+                  C0[k] = fmaf(wgt, orr.y, C0[k]);
+                  C1[k] = fmaf(wgt, gbl.x, C1[k]);
+                  C2[k] = fmaf(wgt, gbl.y, C2[k]);
+                  T[k] = fmaf(-alpha, T[k], T[k]);
+                  last[k] = (uint32_t)b * kBatch + j + u + 1;
+                  if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
+                    fy[k] = kParkedY;
+                    --live;
+                  }
                 }
               }
             }
@@ -175,7 +182,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
         // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
         // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
         // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
-        if ((j & 3) == 3 && __all_sync(0xFFFFFFFFu, live == 0)) break;
+        if (__all_sync(0xFFFFFFFFu, live == 0)) break;
       }
     }
     __syncthreads();  // everyone is done with s_rec[buf] before batch b+2 is gathered into it
