@@ -10,17 +10,30 @@
 // tile rect and the depth order are integer-valued.  Culled Gaussians (z < 0.2) and Gaussians that reach no tile get
 // zero gradients.
 //
-//   blend_bwd      : one CTA per tile, one thread per pixel, the tile list replayed BACK TO FRONT.  T before
-//                    contributor i is recovered as T_{i+1}/(1-alpha_i) from the forward's final T; per-Gaussian
-//                    partial gradients are reduced over the warp with shuffles and added with one atomic per warp.
+//   blend_bwd      : one CTA per tile with the forward kernel's decomposition (64 threads, 4 pixels of one column per
+//                    thread, 128-record batches staged with cp.async), the tile list replayed BACK TO FRONT.  T before
+//                    contributor i is recovered as T_{i+1}/(1-alpha_i) from the forward's final T.  A thread sums the
+//                    raw moments of dL/dpower over its 4 pixels; a warp then reduces 8 of the 9 sums with a
+//                    recursive-halving butterfly (15 shuffles instead of 45) that leaves each sum in a different lane
+//                    group, so ONE atomic instruction adds all nine values: 2 warp reductions per (tile, Gaussian)
+//                    instead of 8, ~4x fewer instructions than the first, one-pixel-per-thread version.
 //   preprocess_bwd : one thread per Gaussian, forward intermediates recomputed from the raw parameters.
 #include "blend_common.cuh"
 #include "gsr_math.cuh"
 
 namespace gsr {
 
-constexpr int kBwdThreads = GSR_TILE * GSR_TILE;
+constexpr int kBwdPX = 4;                        // pixels per thread (one column, rows r, r+4, r+8, r+12)
+constexpr int kBwdThreads = GSR_TILE * GSR_TILE / kBwdPX;
+constexpr int kBwdBatch = 128;                   // records per staged batch
 constexpr int kGradRec = 9;  // d mean2d.x, d mean2d.y, d a, d c, d b (reference conic), d opacity, d r, d g, d b
+constexpr float kBwdParkedY = 1e18f;
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -28,104 +41,206 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sums v[0..7] over the warp by recursive halving: after the exchange with lane^16 a lane keeps four of the sums,
+// after lane^8 two, after lane^4 one; two plain butterfly steps finish it.  Returns sum number
+// 4*bit4(lane) + 2*bit3(lane) + bit2(lane), complete in every lane.
+__device__ __forceinline__ float warp_sum8_scattered(const float v[8], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+  float r[4], s[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+    r[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h3 ? r[i] : r[i + 2], keep = h3 ? r[i + 2] : r[i];
+    s[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
+  }
+  const float send = h2 ? s[0] : s[1], keep = h2 ? s[1] : s[0];
+  float t = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+  t += __shfl_xor_sync(0xFFFFFFFFu, t, 2);
+  t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+  return t;
+}
+
 __global__ void __launch_bounds__(kBwdThreads)
 blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
                  int width, int height, int tiles_x, int row_begin, const float *__restrict__ final_T,
                  const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
                  float *__restrict__ grad_rec) {
-  __shared__ float s_rec[kBwdThreads * GSR_REC_FLOATS];
-  __shared__ uint32_t s_gid[kBwdThreads];
+  constexpr int PX = kBwdPX, THREADS = kBwdThreads, kBatch = kBwdBatch;
+  constexpr int PER = kBatch / THREADS;
+  constexpr int R = GSR_TILE / PX, COLS = 32 / R;  // same lane -> pixel map as the forward kernel
+  __shared__ __align__(16) float s_rec[2][kBatch * GSR_REC_FLOATS];
+  __shared__ uint32_t s_gid[2][kBatch];
   __shared__ uint32_t s_max_last;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
-  const int px = tile_x * GSR_TILE + (tid & (GSR_TILE - 1));
-  const int py = tile_y * GSR_TILE + (tid / GSR_TILE);
-  const bool writable = px < width - 1 && py < height - 1;
+  const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
+  const int py0 = tile_y * GSR_TILE + (lane / COLS);
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
   const uint32_t total = range.y - range.x;
-  const float fx = (float)px, fy = (float)py;
+  const float fx = (float)px;
 
-  float T = 1.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-  uint32_t last = 0;
-  if (writable) {
-    const size_t p = (size_t)py * width + px;
-    T = final_T[p];
-    last = min(n_contrib[p], total);
-    g0 = dL_dimage[p * 3 + 0];
-    g1 = dL_dimage[p * 3 + 1];
-    g2 = dL_dimage[p * 3 + 2];
+  float fy_real[PX], fy[PX], T[PX], g0[PX], g1[PX], g2[PX], behind[PX];
+  uint32_t last[PX];
+  uint32_t my_max = 0;
+#pragma unroll
+  for (int k = 0; k < PX; ++k) {
+    const int py = py0 + k * R;
+    fy_real[k] = (float)py;
+    fy[k] = kBwdParkedY;
+    T[k] = 1.0f;
+    g0[k] = g1[k] = g2[k] = 0.0f;
+    behind[k] = 0.0f;  // sum over contributors behind the current one of alpha_j T_j (c_j . g)
+    last[k] = 0;
+    if (px < width - 1 && py < height - 1) {  // Q8: the reference never writes the last column / row
+      const size_t p = (size_t)py * width + px;
+      T[k] = final_T[p];
+      last[k] = min(n_contrib[p], total);
+      g0[k] = dL_dimage[p * 3 + 0];
+      g1[k] = dL_dimage[p * 3 + 1];
+      g2[k] = dL_dimage[p * 3 + 2];
+    }
+    my_max = max(my_max, last[k]);
   }
   if (tid == 0) s_max_last = 0;
   __syncthreads();
-  atomicMax(&s_max_last, last);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xFFFFFFFFu, my_max, o));
+  if (lane == 0) atomicMax(&s_max_last, my_max);
   __syncthreads();
-  const uint32_t max_last = s_max_last;
-  float behind = 0.0f;  // sum over contributors behind the current one of alpha_j T_j (c_j . g)
+  const uint32_t max_last = s_max_last;  // contributors past it touched no pixel of this tile
+  const int num_batches = (int)((max_last + kBatch - 1) / kBatch);
+  if (num_batches == 0) return;
 
-  const int num_batches = (int)((max_last + kBwdThreads - 1) / kBwdThreads);
-  for (int b = num_batches - 1; b >= 0; --b) {
-    __syncthreads();
-    const uint32_t idx = (uint32_t)b * kBwdThreads + tid;
-    if (idx < max_last) {
-      const uint32_t g = __ldg(gids + range.x + idx);
-      s_gid[tid] = g;
-      const float4 *src = rec + (size_t)g * 3;
-      float4 *dst = reinterpret_cast<float4 *>(s_rec + tid * GSR_REC_FLOATS);
-      dst[0] = __ldg(src);
-      dst[1] = __ldg(src + 1);
-      dst[2] = __ldg(src + 2);
+  // per-lane constants of the reduction's epilogue: which of the nine outputs this lane adds, and its scale
+  const int my_sum = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const float my_scale = (my_sum == 2 || my_sum == 3) ? -0.5f : (my_sum == 4 ? -1.0f : 1.0f);
+  const bool adds = (lane & 3) == 0 || lane == 1;  // lanes 0,4,..,28 add outputs 0..7, lane 1 adds output 8
+
+  // batches are visited last to first: step s handles batch num_batches-1-s
+  uint32_t gnext[PER];
+  auto load_ids = [&](int s) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const uint32_t idx = (uint32_t)(num_batches - 1 - s) * kBatch + r * THREADS + tid;
+      gnext[r] = (s < num_batches && idx < max_last) ? __ldg(gids + range.x + idx) : 0xFFFFFFFFu;
     }
+  };
+  auto issue = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const int slot = r * THREADS + tid;
+      float *dst = &s_rec[buf][slot * GSR_REC_FLOATS];
+      if (gnext[r] != 0xFFFFFFFFu) {
+        const float4 *src = rec + (size_t)gnext[r] * 3;
+        cp_async16(dst, src);
+        cp_async16(dst + 4, src + 1);
+        cp_async16(dst + 8, src + 2);
+        s_gid[buf][slot] = gnext[r];
+      } else {
+        dst[5] = __int_as_float(0x7f800000);  // slot past the end: thr = +inf, no pixel passes the test
+      }
+    }
+    cp_async_commit();
+  };
+  load_ids(0);
+  issue(0);
+  load_ids(1);
+
+  for (int s = 0; s < num_batches; ++s) {
+    const int buf = s & 1;
+    const uint32_t first_idx = (uint32_t)(num_batches - 1 - s) * kBatch;  // list index of slot 0
+    issue(buf ^ 1);  // batch of step s+1 (empty group when past the end)
+    load_ids(s + 2);
+    cp_async_wait<1>();
     __syncthreads();
-    const int count = (int)min((uint32_t)kBwdThreads, max_last - (uint32_t)b * kBwdThreads);
-    for (int j = count - 1; j >= 0; --j) {
-      const float *r = s_rec + j * GSR_REC_FLOATS;
-      const float mx = r[0], my = r[1], A = r[2], C = r[3], B = r[4], thr = r[5], o = r[6];
-      float dmx = 0.f, dmy = 0.f, da = 0.f, dc = 0.f, db = 0.f, dop = 0.f, dr = 0.f, dg = 0.f, dbl = 0.f;
-      bool hit = false;
-      if ((uint32_t)b * kBwdThreads + j < last) {
-        const float dx = fsub(mx, fx), dy = fsub(my, fy);
-        const float power = blend_power(A, C, B, dx, dy);
-        float alpha;
-        if (power >= thr && blend_alpha(power, o, r[10], alpha)) {
-          hit = true;
-          const float one_minus = 1.0f - alpha;
-          T = T / one_minus;  // transmittance in front of this contributor
-          const float wgt = alpha * T;
-          const float cr = r[7], cg = r[8], cb = r[9];
-          dr = wgt * g0;
-          dg = wgt * g1;
-          dbl = wgt * g2;
-          const float cdotg = cr * g0 + cg * g1 + cb * g2;
-          const float dL_dalpha = T * cdotg - behind / one_minus;
-          behind += wgt * cdotg;
-          if (alpha < kMaxDensity) {  // min(o e^p, 0.99): gradient only on the unclamped side
-            const float dL_dpower = alpha * dL_dalpha;
-            dop = (o > 0.0f ? alpha / o : 0.0f) * dL_dalpha;   // d alpha / d o = exp(power)
-            const float a = -2.0f * A, c = -2.0f * C, bb = -B;  // the reference's conic (a, c, b)
-            da = -0.5f * dx * dx * dL_dpower;
-            dc = -0.5f * dy * dy * dL_dpower;
-            db = -dx * dy * dL_dpower;
-            dmx = -(a * dx + bb * dy) * dL_dpower;
-            dmy = -(c * dy + bb * dx) * dL_dpower;
+    const int count = (int)min((uint32_t)kBatch, max_last - first_idx);
+    const int count4 = (count + 3) & ~3;
+    const float *base = s_rec[buf];
+    for (int j = count4 - 4; j >= 0; j -= 4) {
+      // a pixel joins when the walk reaches its last contributor (list index last-1); until then it is parked
+#pragma unroll
+      for (int k = 0; k < PX; ++k) fy[k] = (first_idx + (uint32_t)j < last[k]) ? fy_real[k] : kBwdParkedY;
+#pragma unroll
+      for (int u = 3; u >= 0; --u) {
+        const float *r = base + (j + u) * GSR_REC_FLOATS;
+        const uint32_t lidx = first_idx + (uint32_t)(j + u);
+        const float4 q = *reinterpret_cast<const float4 *>(r);      // mx my A C
+        const float2 w = *reinterpret_cast<const float2 *>(r + 4);  // B thr
+        const float dx = fsub(q.x, fx);
+        const float adx2 = fmul(q.z, fmul(dx, dx));
+        const float bdx = fmul(w.x, dx);
+        float dy[PX], power[PX];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+          dy[k] = fsub(q.y, fy[k]);
+          power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy[k], dy[k]))), fmul(bdx, dy[k]));  // == blend_power, bit for bit
+          any |= power[k] >= w.y;
+        }
+        // sums over this thread's pixels: dL/dpower times (dx, dy, dx^2, dy^2, dx dy), dL/dpower itself, dL/d(r,g,b)
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dblue = 0.f;
+        bool hit = false;
+        if (any) {
+          const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
+          const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
+#pragma unroll
+          for (int k = 0; k < PX; ++k) {
+            if (power[k] >= w.y && lidx < last[k]) {
+              float alpha;
+              if (blend_alpha(power[k], orr.x, gbl.z, alpha)) {  // the forward's keep decision, bit for bit
+                hit = true;
+                const float inv = rcp_approx(1.0f - alpha);  // 1 ulp; T is a product of up to a few hundred of these
+                T[k] *= inv;  // transmittance in front of this contributor
+                const float wgt = alpha * T[k];
+                v[6] = fmaf(wgt, g0[k], v[6]);
+                v[7] = fmaf(wgt, g1[k], v[7]);
+                dblue = fmaf(wgt, g2[k], dblue);
+                const float cdotg = fmaf(orr.y, g0[k], fmaf(gbl.x, g1[k], gbl.y * g2[k]));
+                const float dL_dalpha = fmaf(T[k], cdotg, -behind[k] * inv);
+                behind[k] = fmaf(wgt, cdotg, behind[k]);
+                // min(o e^p, 0.99): gradient only on the unclamped side; d alpha / d power = alpha
+                const float dLp = alpha < kMaxDensity ? alpha * dL_dalpha : 0.0f;
+                const float ux = dx * dLp, uy = dy[k] * dLp;
+                v[0] += ux;
+                v[1] += uy;
+                v[2] = fmaf(dx, ux, v[2]);
+                v[3] = fmaf(dy[k], uy, v[3]);
+                v[4] = fmaf(dx, uy, v[4]);
+                v[5] += dLp;
+              }
+            }
           }
         }
-      }
-      if (__any_sync(0xFFFFFFFFu, hit)) {  // j is warp-uniform: reduce over the warp's 32 pixels, one atomic per value
-        dmx = warp_sum(dmx); dmy = warp_sum(dmy); da = warp_sum(da); dc = warp_sum(dc); db = warp_sum(db);
-        dop = warp_sum(dop); dr = warp_sum(dr); dg = warp_sum(dg); dbl = warp_sum(dbl);
-        if ((tid & 31) == 0) {
-          float *dst = grad_rec + (size_t)s_gid[j] * kGradRec;
-          atomicAdd(dst + 0, dmx); atomicAdd(dst + 1, dmy); atomicAdd(dst + 2, da); atomicAdd(dst + 3, dc);
-          atomicAdd(dst + 4, db); atomicAdd(dst + 5, dop); atomicAdd(dst + 6, dr); atomicAdd(dst + 7, dg);
-          atomicAdd(dst + 8, dbl);
+        if (__any_sync(0xFFFFFFFFu, hit)) {  // converged here: reduce over the warp's 128 pixels
+          const float t = warp_sum8_scattered(v, lane);
+          dblue = warp_sum(dblue);
+          const float s1 = __shfl_sync(0xFFFFFFFFu, t, 0), s2 = __shfl_sync(0xFFFFFFFFu, t, 4);
+          // d mean = (2A dx + B dy, 2C dy + B dx) dL/dpower;  d(a, c, b) = (-dx^2/2, -dy^2/2, -dx dy) dL/dpower;
+          // d opacity = exp(power) dL/dalpha = (alpha / o) dL/dalpha
+          float out = my_scale * t;
+          if (my_sum == 0) out = fmaf(2.0f * q.z, t, w.x * s2);
+          if (my_sum == 1) out = fmaf(2.0f * q.w, t, w.x * s1);
+          if (my_sum == 5) {
+            const float o = r[6];
+            out = o > 0.0f ? t * rcp_approx(o) : 0.0f;
+          }
+          if (lane == 1) out = dblue;
+          if (adds) atomicAdd(grad_rec + (size_t)s_gid[buf][j + u] * kGradRec + (lane == 1 ? 8 : my_sum), out);
         }
       }
     }
+    __syncthreads();  // everyone is done with s_rec[buf] before the batch of step s+2 is gathered into it
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+template <int DEGREE>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
                       const uint32_t *__restrict__ tiles_touched, const float *__restrict__ grad_rec,
@@ -134,14 +249,21 @@ preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera 
                       int64_t dsh_sc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
-  const int degree = cam.sh_degree;
-  const int ncoef = (degree + 1) * (degree + 1);
+  constexpr int degree = DEGREE;  // compile-time: the basis tables below stay in registers
+  constexpr int ncoef = (degree + 1) * (degree + 1);
   float gp[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gop = 0.f;
   const bool touched = (__ldg(tiles_touched + i) & 0x7FFFFFFFu) != 0;  // blended somewhere: everything else gets zeros
   float *dsh = d_sh + i * dsh_sn;
   if (!touched) {
-    for (int k = 0; k < 16; ++k)
-      for (int c = 0; c < 3; ++c) dsh[k * dsh_sk + c * dsh_sc] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float *out = dsh + c * dsh_sc;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        *out = 0.0f;
+        out += dsh_sk;
+      }
+    }
   } else {
     float p[3], ls[3], rot[4];
 #pragma unroll
@@ -190,16 +312,24 @@ preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera 
       basis[15] = kSH3_6 * x * (xx - 3.0f * yy); bx[15] = kSH3_6 * (3.0f * xx - 3.0f * yy); by[15] = kSH3_6 * -6.0f * xy;
     }
     float ddir[3] = {0.f, 0.f, 0.f};
-    const float *shp = g.sh + i * g.sh_sn;
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       float raw = 0.5f, gx = 0.f, gy = 0.f, gz = 0.f;
+      const float *shp = g.sh + i * g.sh_sn + c * g.sh_sc;
+#pragma unroll
       for (int k = 0; k < ncoef; ++k) {
-        const float coef = __ldg(shp + k * g.sh_sk + c * g.sh_sc);
+        const float coef = __ldg(shp);
+        shp += g.sh_sk;
         raw += basis[k] * coef;
         gx += bx[k] * coef; gy += by[k] * coef; gz += bz[k] * coef;
       }
       const float draw = (raw >= 0.0f && raw <= 1.0f) ? drgb[c] : 0.0f;  // clamp(0,1) passes gradient inside only
-      for (int k = 0; k < 16; ++k) dsh[k * dsh_sk + c * dsh_sc] = k < ncoef ? basis[k] * draw : 0.0f;
+      float *out = dsh + c * dsh_sc;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        *out = k < ncoef ? basis[k] * draw : 0.0f;
+        out += dsh_sk;
+      }
       ddir[0] += gx * draw; ddir[1] += gy * draw; ddir[2] += gz * draw;
     }
     {  // dir = d/|d|
@@ -397,8 +527,17 @@ extern "C" int gsr_preprocess_bwd(const gsr_gaussians *g, const gsr_camera *cam,
   GSR_REQUIRE(g && cam && tiles_touched && grad_rec && d_xyz && d_log_scales && d_rots && d_opacity_logit && d_sh,
               "null pointer");
   if (g->n == 0) return GSR_OK;
-  preprocess_bwd_kernel<<<(unsigned)((g->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *g, *cam, tiles_touched, grad_rec, d_xyz, d_log_scales, d_rots, d_opacity_logit, d_sh, dsh_sn, dsh_sk, dsh_sc);
+  GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
+#define GSR_PRE_BWD(D)                                                                                     \
+  preprocess_bwd_kernel<D><<<(unsigned)((g->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(              \
+      *g, *cam, tiles_touched, grad_rec, d_xyz, d_log_scales, d_rots, d_opacity_logit, d_sh, dsh_sn, dsh_sk, dsh_sc)
+  switch (cam->sh_degree) {
+    case 0: GSR_PRE_BWD(0); break;
+    case 1: GSR_PRE_BWD(1); break;
+    case 2: GSR_PRE_BWD(2); break;
+    default: GSR_PRE_BWD(3); break;
+  }
+#undef GSR_PRE_BWD
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

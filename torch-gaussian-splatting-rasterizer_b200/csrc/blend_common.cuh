@@ -30,4 +30,15 @@ __device__ __forceinline__ bool blend_alpha(float power, float opacity, float lo
   return alpha > kMinAlpha && power <= 0.0f;  // :291
 }
 
+// cp.async (LDGSTS) staging helpers shared by the forward and backward blend kernels
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 }  // namespace gsr
