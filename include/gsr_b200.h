@@ -170,8 +170,9 @@ int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const uint32_t *t
  * spherical_harmonics.py:27-73)
  * --------------------------------------------------------------------------------------------- */
 /* Blend backward: the tile lists replayed back to front.  final_T / n_contrib are the forward's outputs,
- * dL_dimage[H,W,3] the incoming gradient; grad_rec[n,9] (zeroed by the caller) accumulates per Gaussian
- * d mean2d.xy, d conic (a,c,b), d opacity (activated), d rgb. */
+ * dL_dimage[H,W,3] the incoming gradient; grad_rec[n,9] (zeroed by the caller) accumulates per Gaussian the sums
+ * over its pixels of dL/dpower x (dx, dy, dx^2, dy^2, dx dy, 1) and dL/d(r,g,b) - everything the blend contributes
+ * to d mean2d, d conic and d opacity is linear in them; gsr_preprocess_bwd does that conversion. */
 int gsr_blend_bwd(const float *rec, const uint32_t *tile_gids, const uint32_t *tile_ranges, int32_t width,
                   int32_t height, int32_t tile_row_begin, int32_t tile_row_end, const float *final_T,
                   const uint32_t *n_contrib, const float *dL_dimage, float *grad_rec, void *stream);

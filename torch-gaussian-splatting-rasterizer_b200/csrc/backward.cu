@@ -26,7 +26,10 @@ namespace gsr {
 constexpr int kBwdPX = 4;                        // pixels per thread (one column, rows r, r+4, r+8, r+12)
 constexpr int kBwdThreads = GSR_TILE * GSR_TILE / kBwdPX;
 constexpr int kBwdBatch = 128;                   // records per staged batch
-constexpr int kGradRec = 9;  // d mean2d.x, d mean2d.y, d a, d c, d b (reference conic), d opacity, d r, d g, d b
+// grad_rec row: sums over the pixels a Gaussian was blended into of dL/dpower x (dx, dy, dx^2, dy^2, dx dy, 1), then
+// dL/d(r, g, b).  Everything the blend contributes is linear in these, so the conversion to d mean2d, d conic and
+// d opacity happens once per Gaussian in preprocess_bwd instead of once per (warp, Gaussian) here.
+constexpr int kGradRec = 9;
 constexpr float kBwdParkedY = 1e18f;
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -116,9 +119,8 @@ blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gi
   const int num_batches = (int)((max_last + kBatch - 1) / kBatch);
   if (num_batches == 0) return;
 
-  // per-lane constants of the reduction's epilogue: which of the nine outputs this lane adds, and its scale
+  // which of the nine sums this lane adds to grad_rec after the warp reduction
   const int my_sum = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const float my_scale = (my_sum == 2 || my_sum == 3) ? -0.5f : (my_sum == 4 ? -1.0f : 1.0f);
   const bool adds = (lane & 3) == 0 || lane == 1;  // lanes 0,4,..,28 add outputs 0..7, lane 1 adds output 8
 
   // batches are visited last to first: step s handles batch num_batches-1-s
@@ -219,17 +221,7 @@ blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gi
         if (__any_sync(0xFFFFFFFFu, hit)) {  // converged here: reduce over the warp's 128 pixels
           const float t = warp_sum8_scattered(v, lane);
           dblue = warp_sum(dblue);
-          const float s1 = __shfl_sync(0xFFFFFFFFu, t, 0), s2 = __shfl_sync(0xFFFFFFFFu, t, 4);
-          // d mean = (2A dx + B dy, 2C dy + B dx) dL/dpower;  d(a, c, b) = (-dx^2/2, -dy^2/2, -dx dy) dL/dpower;
-          // d opacity = exp(power) dL/dalpha = (alpha / o) dL/dalpha
-          float out = my_scale * t;
-          if (my_sum == 0) out = fmaf(2.0f * q.z, t, w.x * s2);
-          if (my_sum == 1) out = fmaf(2.0f * q.w, t, w.x * s1);
-          if (my_sum == 5) {
-            const float o = r[6];
-            out = o > 0.0f ? t * rcp_approx(o) : 0.0f;
-          }
-          if (lane == 1) out = dblue;
+          const float out = lane == 1 ? dblue : t;
           if (adds) atomicAdd(grad_rec + (size_t)s_gid[buf][j + u] * kGradRec + (lane == 1 ? 8 : my_sum), out);
         }
       }
@@ -274,12 +266,12 @@ preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera 
     for (int c = 0; c < 4; ++c) rot[c] = __ldg(g.rots + i * g.rot_sn + c * g.rot_sc);
     const float logit = __ldg(g.opacity_logit + i * g.opacity_sn);
     const float *gr = grad_rec + i * kGradRec;
-    const float dmean_x = gr[0], dmean_y = gr[1], da = gr[2], dc = gr[3], db = gr[4], dopac = gr[5];
+    const float m_x = gr[0], m_y = gr[1], m_xx = gr[2], m_yy = gr[3], m_xy = gr[4], m_1 = gr[5];  // moments of dL/dpower
     const float drgb[3] = {gr[6], gr[7], gr[8]};
 
-    // ---- opacity = sigmoid(logit) ----
+    // ---- opacity = sigmoid(logit); alpha = o e^power, so dL/do = sum(dL/dpower) / o ----
     const float o = sigmoid_ref(logit);
-    gop = dopac * o * (1.0f - o);
+    gop = m_1 * (1.0f - o);
 
     // ---- colour: rgb_c = clamp(sum_k basis_k(dir) sh[k][c] + 0.5, 0, 1) ----
     float dirv[3] = {p[0] - cam.cam_center[0], p[1] - cam.cam_center[1], p[2] - cam.cam_center[2]};
@@ -348,6 +340,17 @@ preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera 
     float S[9], c2[4];
     covariance3d(ls, rot, S);
     covariance2d(S, camp, cam, c2);
+
+    // ---- power = -(a dx^2 + c dy^2)/2 - b dx dy with d = mean2d - pixel: the blend's moments become
+    //      d mean2d = -(a m_x + b m_y, c m_y + b m_x), d(a, c, b) = (-m_xx/2, -m_yy/2, -m_xy) ----
+    float dmean_x = 0.f, dmean_y = 0.f;
+    const float da = -0.5f * m_xx, dc = -0.5f * m_yy, db = -m_xy;
+    {
+      float ca, cc, cb;
+      conic_from_cov(c2, ca, cc, cb);
+      dmean_x = -(ca * m_x + cb * m_y);
+      dmean_y = -(cc * m_y + cb * m_x);
+    }
 
     // ---- mean2d = ((clip.xy * pw + 1) * (W,H) - 1) / 2, pw = 1/(clip.w + 1e-7) ----
     float dclip[4] = {0.f, 0.f, 0.f, 0.f};
