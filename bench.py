@@ -363,47 +363,52 @@ def main():
                         "note": "algorithmic bytes = SURVEY 8(d) formula for a 64-bit-key LSD sort; this design moves fewer"}}
         del pre, binned, out
 
-        # ---- end to end: host tensors in (pinned), host image out, through the public render() ----
-        if world == 1:
-            host = [torch.from_numpy(a).pin_memory() for a in (cloud.xyz, cloud.scales, cloud.rots, cloud.opacity)]
-            sh_host = torch.from_numpy(cloud.sh_planar()).pin_memory().permute(2, 1, 0)
-            img_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-            v = views[0]
-            h2d = sum(t.numel() * 4 for t in host) + sh_host.numel() * 4
-            d2h = img_host.numel() * 4
+    # ---- end to end: host tensors in (pinned), host image out, through the public render() ----
+    # every rank uploads ITS copy of the scene, renders ITS view and reads ITS image back; the job's value is the
+    # sum over ranks, timed as the max over ranks between two barriers
+    host = [torch.from_numpy(a).pin_memory() for a in (cloud.xyz, cloud.scales, cloud.rots, cloud.opacity)]
+    sh_host = torch.from_numpy(cloud.sh_planar()).pin_memory().permute(2, 1, 0)
+    img_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    v = views[rank % len(views)]
+    h2d = sum(t.numel() * 4 for t in host) + sh_host.numel() * 4
+    d2h = img_host.numel() * 4
 
-            def e2e_step():
-                img = R.render(host[0], host[1], host[2], host[3], sh_host, v.qvec, v.tvec, intr.fx, intr.fy,
-                               intr.cam_width, intr.cam_height, W, H, degree, renderer=renderer)
-                img_host.copy_(img, non_blocking=True)
-                torch.cuda.synchronize()
+    def e2e_step():
+        img = R.render(host[0], host[1], host[2], host[3], sh_host, v.qvec, v.tvec, intr.fx, intr.fy,
+                       intr.cam_width, intr.cam_height, W, H, degree, renderer=renderer)
+        img_host.copy_(img, non_blocking=True)
+        torch.cuda.synchronize()
 
-            for _ in range(2):
-                e2e_step()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                e2e_step()
-            dt = (time.perf_counter() - t0) / args.e2e_steps
-            # for context: the same loop with the scene resident (only the 176-byte camera goes up, the image comes down)
-            def resident_step():
-                renderer.render(model, cams[0], out=frame, check=False)
-                img_host.copy_(frame, non_blocking=True)
-                torch.cuda.synchronize()
+    def resident_step():
+        renderer.render(model, cams[rank % len(cams)], out=frame, check=False)
+        img_host.copy_(frame, non_blocking=True)
+        torch.cuda.synchronize()
 
-            for _ in range(2):
-                resident_step()
-            t0 = time.perf_counter()
-            for _ in range(4 * args.e2e_steps):
-                resident_step()
-            dt_res = (time.perf_counter() - t0) / (4 * args.e2e_steps)
-            line["e2e"] = {"value": W * H / 1e6 / dt, "unit": "MPix/s", "fps": 1.0 / dt, "ms_per_step": dt * 1e3,
-                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                           "what": "rasterize.render(host tensors) -> host image: uploads all Gaussian parameters every step",
-                           "resident_scene": {"fps": 1.0 / dt_res, "ms_per_step": dt_res * 1e3, "h2d_bytes_per_step": 176,
-                                              "d2h_bytes_per_step": d2h,
-                                              "what": "scene kept in HBM between steps (video / serving use): camera up, image down"}}
-        else:
-            line["e2e"] = None
+    def timed(step, n):
+        for _ in range(2):
+            step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        t = torch.tensor([(time.perf_counter() - t0) / n], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dt = timed(e2e_step, args.e2e_steps)
+    # for context: the same loop with the scene resident (only the 176-byte camera goes up, the image comes down)
+    dt_res = timed(resident_step, 4 * args.e2e_steps)
+    if rank == 0:
+        line["e2e"] = {"value": world * W * H / 1e6 / dt, "unit": "MPix/s", "fps": world / dt, "ms_per_step": dt * 1e3,
+                       "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                       "what": "rasterize.render(host tensors) -> host image on every rank: uploads all Gaussian "
+                               "parameters every step (PCIe-bound); whole-job sum, max over ranks",
+                       "resident_scene": {"fps": world / dt_res, "ms_per_step": dt_res * 1e3,
+                                          "h2d_bytes_per_step": 176 * world, "d2h_bytes_per_step": d2h * world,
+                                          "what": "scene kept in HBM between steps (video / serving use): camera up, image down"}}
+    if rank == 0:
         line["clocks"] = clocks.summary()
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -69,7 +69,17 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     tt = pre["tiles_touched"].view(np.uint32)
     assert np.array_equal((tt >> 31) == 1, o["skip"] == 0)
     r = pre["rect"].astype(np.int64)
-    assert ((tt & 0x7FFFFFFF) <= (r[:, 2] - r[:, 0]) * (r[:, 3] - r[:, 1]))[o["skip"] == 0].all()
+    area = (r[:, 2] - r[:, 0]) * (r[:, 3] - r[:, 1])
+    assert ((tt & 0x7FFFFFFF) <= area)[o["skip"] == 0].all()
+    # the 16-byte tile span alone determines the pair count (what the binning stage gathers): set bits of the keep
+    # mask within the rect for rects of <= 64 tiles, the whole area above
+    mask = pre["tile_mask"].view(np.uint32).astype(np.uint64)
+    mask64 = mask[:, 0] | (mask[:, 1] << np.uint64(32))
+    inside = np.where(area >= 64, np.uint64(0xFFFFFFFFFFFFFFFF), (np.uint64(1) << np.minimum(area, 63).astype(np.uint64)) - np.uint64(1))
+    pop = np.array([bin(int(m)).count("1") for m in (mask64 & inside)])
+    from_span = np.where(area <= 64, pop, area)
+    vis = o["skip"] == 0
+    assert np.array_equal(from_span[vis], (tt & 0x7FFFFFFF)[vis].astype(np.int64))
 
 
 @pytest.mark.parametrize("n,bits", [(1, 32), (255, 32), (4096, 32), (4097, 32), (100_003, 32), (1_000_000, 32),
