@@ -184,6 +184,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
+    ap.add_argument("--orbit", action="store_true", help="N=1 only: render the 256-view orbit of the N>1 workload (to separate view cost from scaling loss)")
+    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p", help="N>1: how finished frames are all-gathered")
+    ap.add_argument("--ring", type=int, default=8, help="frame buffers per rank (N>1): how far a rank may run ahead of the gather")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -214,7 +217,7 @@ def main():
     renderer = R.Renderer()
     n_streams = max(1, args.streams)
     lanes = [(renderer, torch.cuda.current_stream())] + [(R.Renderer(), torch.cuda.Stream()) for _ in range(n_streams - 1)]
-    if world == 1:
+    if world == 1 and not args.orbit:
         views = [scenes.front_view(0)]
     else:
         views = scenes.orbit_views(256)
@@ -226,7 +229,12 @@ def main():
     frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
     gathered = torch.empty((world, H, W, 3), dtype=torch.float32, device="cuda") if world > 1 else None
     comm = torch.cuda.Stream() if world > 1 else None
-    n_buf = 2 * n_streams
+    peer = None
+    if world > 1 and args.gather == "p2p":
+        from gsr_b200.dist import PeerGather
+        peer = PeerGather.create((H, W, 3), "cuda", slots=4)
+    gather_kind = "p2p-dma" if peer is not None else ("nccl" if world > 1 else None)
+    n_buf = max(args.ring, n_streams)  # frames a rank may run ahead of the slowest rank's gather
     frames = [torch.empty_like(frame) for _ in range(n_buf)]
     gathered_ev = [None] * n_buf
 
@@ -243,7 +251,10 @@ def main():
                 done = torch.cuda.Event(); done.record(strm)
                 comm.wait_event(done)
                 with torch.cuda.stream(comm):
-                    dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1))
+                    if peer is not None:  # copy-engine gather over NVLink (gsr_b200.dist.PeerGather): no SM time
+                        peer.push(buf, i % peer.slots)
+                    else:
+                        dist.all_gather_into_tensor(gathered.view(-1), buf.view(-1))
                     gathered_ev[i % n_buf] = torch.cuda.Event(); gathered_ev[i % n_buf].record(comm)
 
     def fork():   # side lanes start after everything already queued on the main stream
@@ -300,7 +311,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("C3: 3M synth_v1 Gaussians (seed 3), SH degree 3, 1920x1080, front view" if world == 1
                                     else f"C4: same 3M-Gaussian scene replicated per GPU, 256-view orbit sharded by view "
-                                         f"(rank r renders view step*{world}+r), frames all-gathered with NCCL"),
+                                         f"(rank r renders view step*{world}+r), frames all-gathered ({gather_kind})"),
                        "n_gaussians": cloud.n, "width": W, "height": H, "sh_degree": degree,
                        "l2_policy": "inputs (708 MB of Gaussian parameters) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"view-sharded x{world}" if world > 1 else "single GPU",
