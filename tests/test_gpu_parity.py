@@ -328,6 +328,14 @@ def test_run_rasterization_cli_on_scene_dir(tmp_path, golden):
     import os
 
     assert os.path.exists(os.path.join(out, "render.png"))
+    # the reference's closing figure (render above the photo) as a file + numbers; frame-sequence writer
+    assert os.path.exists(os.path.join(out, "comparison.png"))
+    cmp = rasterize.run_rasterization.last_comparison
+    assert np.isfinite(cmp["mae"]) and cmp["psnr_db"] > 0
+    frames = torch.from_numpy(np.stack([img, img[::-1].copy()]))
+    assert rasterize.write_frame_sequence(frames, os.path.join(out, "orbit")) == 2
+    assert sorted(os.listdir(os.path.join(out, "orbit"))) == ["frame_0000000.png", "frame_0000001.png"]
+    assert rasterize.psnr(frames[0], frames[0]) == float("inf") and rasterize.psnr(frames[0], frames[1]) < 60
     with pytest.raises(KeyError):  # scene_index is a COLMAP image_id (Q17)
         rasterize.run_rasterization.callback(input_dir=root, trained_model_path=root, output_path=out, scene_index=5,
                                              scale_factor=2, generate_video=False)

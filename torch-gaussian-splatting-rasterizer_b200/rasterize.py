@@ -164,6 +164,50 @@ def _save_png(image: torch.Tensor, path: str) -> None:
     Image.fromarray((image.clamp(0, 1).cpu().numpy() * 255.0).astype(np.uint8)).save(path)
 
 
+def psnr(image: torch.Tensor, reference: torch.Tensor) -> float:
+    """PSNR (dB, peak 1.0) of two ``[H,W,3]`` images in [0,1]; ``inf`` for identical images."""
+    mse = torch.mean((image.float().clamp(0, 1) - reference.to(image.device).float().clamp(0, 1)) ** 2).item()
+    return float("inf") if mse == 0 else -10.0 * math.log10(mse)
+
+
+def compare_with_ground_truth(image: torch.Tensor, gt_img_path: str, out_path: Optional[str] = None) -> dict:
+    """What the reference shows in a matplotlib window (:468-476: the render above the ground-truth photo), as numbers
+    and an optional PNG: PSNR / mean absolute error against the photo (resized to the render if needed), and the two
+    images stacked vertically in ``out_path``."""
+    from PIL import Image
+
+    H, W = image.shape[:2]
+    gt = Image.open(gt_img_path).convert("RGB")
+    if gt.size != (W, H):
+        gt = gt.resize((W, H), Image.BILINEAR)
+    gt_t = torch.from_numpy(np.asarray(gt, dtype=np.float32) / 255.0)
+    img = image.detach().float().clamp(0, 1).cpu()
+    out = {"psnr_db": psnr(img, gt_t), "mae": float((img - gt_t).abs().mean())}
+    if out_path:
+        both = torch.cat([img, gt_t], dim=0)
+        Image.fromarray((both.numpy() * 255.0).astype(np.uint8)).save(out_path)
+    return out
+
+
+def write_frame_sequence(frames: torch.Tensor, out_dir: str, prefix: str = "frame_", video: bool = False,
+                         framerate: int = 20) -> int:
+    """``frames[V,H,W,3]`` (e.g. ``gsr_b200.dist.render_orbit``) -> ``<out_dir>/<prefix>0000000.png`` ...; with
+    ``video=True`` and ffmpeg on PATH also ``<out_dir>/video_render.mp4`` (same encoder settings as :465)."""
+    os.makedirs(out_dir, exist_ok=True)
+    for i in range(frames.shape[0]):
+        _save_png(frames[i], os.path.join(out_dir, f"{prefix}{str(i).zfill(7)}.png"))
+    if video:
+        if shutil.which("ffmpeg"):
+            H, W = frames.shape[1:3]
+            subprocess.run(["ffmpeg", "-y", "-framerate", str(framerate), "-pattern_type", "glob", "-i",
+                            os.path.join(out_dir, f"{prefix}*.png"), "-r", "10", "-vcodec", "libx264", "-s",
+                            f"{W - W % 2}x{H - H % 2}", "-pix_fmt", "yuv420p",
+                            os.path.join(out_dir, "video_render.mp4")], check=True)
+        else:
+            logger.warning("ffmpeg not found: %d frames written to %s, no video encoded", frames.shape[0], out_dir)
+    return int(frames.shape[0])
+
+
 @click.command()
 @click.option("--input_dir", type=str, default="")
 @click.option("--trained_model_path", type=str, default="")
@@ -186,9 +230,14 @@ def run_rasterization(input_dir: str, trained_model_path, output_path: Optional[
     renderer = Renderer()
     image = renderer.render(model, cam)
     run_rasterization.last_image = image  # handle for callers that drive the command programmatically
+    gt_img_path = os.path.join(input_dir, f"images_{scale_factor}", scene.name)
     if output_path:
         os.makedirs(output_path, exist_ok=True)
         _save_png(image, os.path.join(output_path, "render.png"))
+        # the reference's closing figure (:468-476), as a file and two numbers
+        cmp = compare_with_ground_truth(image, gt_img_path, os.path.join(output_path, "comparison.png"))
+        logger.info("render vs %s: PSNR %.2f dB, MAE %.4f", scene.name, cmp["psnr_db"], cmp["mae"])
+        run_rasterization.last_comparison = cmp
     if generate_video:
         frames = os.path.join(output_path, "images")
         os.makedirs(frames, exist_ok=True)
