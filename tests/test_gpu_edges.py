@@ -133,3 +133,35 @@ def test_ply_device_loader_matches_column_loader(tmp_path):
     m2 = R.GaussianModel.from_ply(path2)
     for a, b in ((m2.xyz, ref.xyz), (m2.rots, ref.rots), (m2.opacity, ref.opacity), (m2.sh, ref.sh)):
         assert torch.equal(a, b)
+
+
+_PX_SCRIPT = r"""
+import os, sys, numpy as np, torch
+root = sys.argv[1]
+sys.path[:0] = [os.path.join(root, "torch-gaussian-splatting-rasterizer_b200"), root]
+from gsr_b200 import camera, scenes, render as R
+cloud = scenes.synth_v1(40_000, 11, scale_factor=0.5)
+intr = scenes.Intrinsics.synthetic(403, 277)
+cam = camera.camera_for(intr, scenes.orbit_views(1, total=7, first=3)[0], 3)
+img = R.Renderer().render(R.GaussianModel.from_cloud(cloud), cam)
+np.save(sys.argv[2], img.cpu().numpy())
+"""
+
+
+def test_packed_fp32_blend_is_bit_identical_to_the_scalar_kernel(tmp_path):
+    """The 4-pixel kernel evaluates `power` with Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2); the
+    2-pixel instantiation is the scalar code.  Same pixels, same Gaussians, same order: the images must be equal bit
+    for bit (a contracted multiply-add in the packed path would show up here)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for px in ("2", "4"):
+        path = str(tmp_path / f"px{px}.npy")
+        env = dict(os.environ, GSR_BLEND_PX=px)
+        subprocess.run([sys.executable, "-c", _PX_SCRIPT, root, path], check=True, env=env, timeout=600)
+        out[px] = np.load(path)
+    assert out["4"].max() > 0.1
+    assert np.array_equal(out["2"].view(np.uint32), out["4"].view(np.uint32))

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256 / PX)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
-             uint32_t *__restrict__ n_contrib, gsr_frame_info *info) {
+             uint32_t *__restrict__ n_contrib, gsr_frame_info *info, float neg_zero) {
   constexpr int THREADS = 256 / PX;
   constexpr int kBatch = PX >= 8 ? 64 : 128;  // records per staged batch (smaller CTAs keep more CTAs resident)
   constexpr int PER = kBatch / THREADS;  // records gathered per thread and batch
@@ -66,6 +66,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     last[k] = 0;
   }
   unsigned long long my_iters = 0, my_evals = 0;
+  // -0.0f, but only the host knows (kernel argument): ptxas folds fma(a, b, -0) back into a contractable multiply
+  const f32x2 neg_zero2 = pack2(neg_zero, neg_zero);
 
   const uint32_t total = range.y - range.x;
   const int num_batches = (int)((total + kBatch - 1) / kBatch);
@@ -139,12 +141,27 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           const float bdx = fmul(w.x, dx);
           float power[PX];
           bool any = false;
+          if (PX == 4) {
+            // the four pixels as two packed pairs: 6 FADD2/FMUL2/FFMA2 per pair instead of 12 scalar operations, every
+            // half rounded like the scalar code (blend_common.cuh)
+            const f32x2 my2 = pack2(q.y, q.y), c2 = pack2(q.w, q.w), a2 = pack2(adx2, adx2), b2 = pack2(bdx, bdx);
 #pragma unroll
-          for (int k = 0; k < PX; ++k) {
-            const float dy = fsub(q.y, fy[k]);
-            // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
-            power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
-            any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
+            for (int h = 0; h < 2; ++h) {
+              const f32x2 dy = sub2(my2, pack2(fy[2 * h], fy[2 * h + 1]));
+              const f32x2 cdy2 = mul2_exact(c2, mul2(dy, dy), neg_zero2);
+              const f32x2 p = add2(add2(a2, cdy2), mul2_exact(b2, dy, neg_zero2));
+              unpack2(p, power[2 * h], power[2 * h + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k < PX; ++k) any |= power[k] >= w.y;
+          } else {
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+              const float dy = fsub(q.y, fy[k]);
+              // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
+              power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
+              any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
+            }
           }
           if (any) {
             const float2 orr = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 6);  // opacity r
@@ -259,7 +276,7 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
 #define GSR_BLEND_LAUNCH(PX, COUNT, RANKED)                                                                        \
   blend_kernel<PX, COUNT, RANKED><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                                     \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
-      blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev)
+      blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
 #define GSR_BLEND_PICK(PX)                                                          \
   do {                                                                              \
     if (blend_rank) {                                                               \

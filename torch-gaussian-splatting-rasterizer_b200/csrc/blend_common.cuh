@@ -30,6 +30,42 @@ __device__ __forceinline__ bool blend_alpha(float power, float opacity, float lo
   return alpha > kMinAlpha && power <= 0.0f;  // :291
 }
 
+
+// ---- packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2: two independent IEEE single operations per instruction) --------
+// One issue slot does the work of two, each half rounded exactly like the scalar operation, so results are bit-identical
+// to the scalar code.  ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (it honours neither the
+// .rn qualifiers nor -fmad=false for the packed forms), which would drop a rounding the reference performs: products
+// that feed an addition are therefore written as fma(a, b, -0), which cannot be contracted and equals round(a*b).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 v;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b));
+  return v;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 v;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b));
+  return v;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {  // only where the product does not feed an add/sub
+  f32x2 v;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(a), "l"(b));
+  return v;
+}
+__device__ __forceinline__ f32x2 mul2_exact(f32x2 a, f32x2 b, f32x2 neg_zero) {  // round(a*b), never contracted
+  f32x2 v;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(a), "l"(b), "l"(neg_zero));
+  return v;
+}
+
 // cp.async (LDGSTS) staging helpers shared by the forward and backward blend kernels
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
