@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(kBwdThreads)
 blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
                  int width, int height, int tiles_x, int row_begin, const float *__restrict__ final_T,
                  const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dimage,
-                 float *__restrict__ grad_rec) {
+                 float *__restrict__ grad_rec, float neg_zero) {
+  static_assert(kBwdPX == 4, "blend_power4 evaluates four pixels");
+  const f32x2 neg_zero2 = pack2(neg_zero, neg_zero);  // -0.0f from the host: see blend_common.cuh
   constexpr int PX = kBwdPX, THREADS = kBwdThreads, kBatch = kBwdBatch;
   constexpr int PER = kBatch / THREADS;
   constexpr int R = GSR_TILE / PX, COLS = 32 / R;  // same lane -> pixel map as the forward kernel
@@ -178,12 +180,9 @@ blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gi
         const float bdx = fmul(w.x, dx);
         float dy[PX], power[PX];
         bool any = false;
+        blend_power4(q.y, q.w, adx2, bdx, fy, neg_zero2, dy, power);  // packed FP32, == blend_power bit for bit
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-          dy[k] = fsub(q.y, fy[k]);
-          power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy[k], dy[k]))), fmul(bdx, dy[k]));  // == blend_power, bit for bit
-          any |= power[k] >= w.y;
-        }
+        for (int k = 0; k < PX; ++k) any |= power[k] >= w.y;
         // sums over this thread's pixels: dL/dpower times (dx, dy, dx^2, dy^2, dx dy), dL/dpower itself, dL/d(r,g,b)
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dblue = 0.f;
         bool hit = false;
@@ -518,7 +517,7 @@ extern "C" int gsr_blend_bwd(const float *rec, const uint32_t *tile_gids, const 
   dim3 grid(tg.tiles_x, tile_row_end - tile_row_begin);
   blend_bwd_kernel<<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>((const float4 *)rec, tile_gids,
                                                                   (const uint2 *)tile_ranges, width, height, tg.tiles_x,
-                                                                  tile_row_begin, final_T, n_contrib, dL_dimage, grad_rec);
+                                                                  tile_row_begin, final_T, n_contrib, dL_dimage, grad_rec, -0.0f);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
 }

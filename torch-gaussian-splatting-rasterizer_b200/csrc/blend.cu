@@ -144,14 +144,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           if (PX == 4) {
             // the four pixels as two packed pairs: 6 FADD2/FMUL2/FFMA2 per pair instead of 12 scalar operations, every
             // half rounded like the scalar code (blend_common.cuh)
-            const f32x2 my2 = pack2(q.y, q.y), c2 = pack2(q.w, q.w), a2 = pack2(adx2, adx2), b2 = pack2(bdx, bdx);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const f32x2 dy = sub2(my2, pack2(fy[2 * h], fy[2 * h + 1]));
-              const f32x2 cdy2 = mul2_exact(c2, mul2(dy, dy), neg_zero2);
-              const f32x2 p = add2(add2(a2, cdy2), mul2_exact(b2, dy, neg_zero2));
-              unpack2(p, power[2 * h], power[2 * h + 1]);
-            }
+            float dy[4];
+            blend_power4(q.y, q.w, adx2, bdx, fy, neg_zero2, dy, power);
 #pragma unroll
             for (int k = 0; k < PX; ++k) any |= power[k] >= w.y;
           } else {

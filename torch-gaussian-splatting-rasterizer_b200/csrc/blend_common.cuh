@@ -66,6 +66,22 @@ __device__ __forceinline__ f32x2 mul2_exact(f32x2 a, f32x2 b, f32x2 neg_zero) { 
   return v;
 }
 
+// power of four pixels of one column (shared dx), two packed pairs: (A dx^2 + C dy^2) + (B dx) dy in the reference's
+// operation order (rasterize.py:280-283), each half rounded like the scalar blend_power.  `neg_zero2` must be a
+// packed -0.0f the compiler cannot see through (see above).
+__device__ __forceinline__ void blend_power4(float my, float C, float adx2, float bdx, const float fy[4],
+                                             f32x2 neg_zero2, float dy_out[4], float power[4]) {
+  const f32x2 my2 = pack2(my, my), c2 = pack2(C, C), a2 = pack2(adx2, adx2), b2 = pack2(bdx, bdx);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const f32x2 dy = sub2(my2, pack2(fy[2 * h], fy[2 * h + 1]));
+    const f32x2 cdy2 = mul2_exact(c2, mul2(dy, dy), neg_zero2);
+    const f32x2 p = add2(add2(a2, cdy2), mul2_exact(b2, dy, neg_zero2));
+    unpack2(dy, dy_out[2 * h], dy_out[2 * h + 1]);
+    unpack2(p, power[2 * h], power[2 * h + 1]);
+  }
+}
+
 // cp.async (LDGSTS) staging helpers shared by the forward and backward blend kernels
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
