@@ -345,11 +345,26 @@ constexpr int kRangeThreads = 256;
 __global__ void __launch_bounds__(kRangeThreads)
 tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, const BinCounters *ctr, uint2 *__restrict__ ranges) {
   const uint32_t n = ctr->n_dup;
-  const uint32_t stride = gridDim.x * kRangeThreads;
-  for (uint32_t i = blockIdx.x * kRangeThreads + threadIdx.x; i < n; i += stride) {
-    const uint32_t t = __ldg(sorted_tiles + i);
-    if (i == 0 || __ldg(sorted_tiles + i - 1) != t) ranges[t].x = i;
-    if (i == n - 1 || __ldg(sorted_tiles + i + 1) != t) ranges[t].y = i + 1;
+  const uint32_t stride = gridDim.x * kRangeThreads * 4;
+  // four consecutive ids per thread (one 16-byte load) plus the two neighbours of the quad
+  for (uint32_t i = (blockIdx.x * kRangeThreads + threadIdx.x) * 4; i < n; i += stride) {
+    uint32_t t[6];
+    if (i + 4 <= n) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(sorted_tiles + i));
+      t[1] = q.x; t[2] = q.y; t[3] = q.z; t[4] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[1 + k] = i + k < n ? __ldg(sorted_tiles + i + k) : 0xFFFFFFFFu;
+    }
+    t[0] = i > 0 ? __ldg(sorted_tiles + i - 1) : 0xFFFFFFFFu;       // no tile id equals the sentinel
+    t[5] = i + 4 < n ? __ldg(sorted_tiles + i + 4) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i + k < n) {
+        if (t[k] != t[k + 1]) ranges[t[k + 1]].x = i + k;
+        if (t[k + 2] != t[k + 1]) ranges[t[k + 1]].y = i + k + 1;
+      }
+    }
   }
 }
 
@@ -461,8 +476,8 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   if (rc) return rc;
 
   // 4. tile ranges from the sorted ids
-  const int64_t want = ceil_div64(max_dup, kRangeThreads * 4);
-  tile_ranges_kernel<<<(unsigned)(want > 148 * 8 ? 148 * 8 : (want > 0 ? want : 1)), kRangeThreads, 0, stream>>>(
+  const int64_t want = ceil_div64(max_dup, kRangeThreads * 4);  // four ids per thread
+  tile_ranges_kernel<<<(unsigned)(want > 148 * 16 ? 148 * 16 : (want > 0 ? want : 1)), kRangeThreads, 0, stream>>>(
       sorted_tiles, ctr, (uint2 *)tile_ranges);
   GSR_LAUNCH_CHECK();
   return GSR_OK;
