@@ -163,11 +163,13 @@ def run_reference_arm(args):
     for _ in range(max(1, min(args.steps, 2))):
         vals.append(cpu_baseline(cloud, intr, degree, budget_s=args.cpu_budget))
     b = vals[-1]
-    line = {"impl": "reference", "metric": "MPix/s, 3M-Gaussian SH3 @1080p (reference CPU render, oracle port)",
+    # same metric / unit / workload strings as our arm: the driver divides one line by the other
+    line = {"impl": "reference", "metric": "MPix/s, 3M-Gaussian SH3 @1080p render",
+            "what": "the reference's CPU render timed through the oracle's torch port (the reference is Python and cannot travel to the GPU box)",
             "value": b["value"], "unit": "MPix/s", "fps": b["value"] * 1e6 / (intr.width * intr.height),
             "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": b["est_seconds_per_frame"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: 3M synth_v1 Gaussians, SH degree 3, 1920x1080, front view" if args.n is None
+            "config": {"workload": "C3: 3M synth_v1 Gaussians (seed 3), SH degree 3, 1920x1080, front view" if args.n is None
                        else f"C3 scene with n={args.n}"},
             "cpu_baseline": b, "e2e": {"value": b["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0,
                                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
