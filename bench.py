@@ -169,7 +169,10 @@ def run_reference_arm(args):
             "value": b["value"], "unit": "MPix/s", "fps": b["value"] * 1e6 / (intr.width * intr.height),
             "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": b["est_seconds_per_frame"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: 3M synth_v1 Gaussians (seed 3), SH degree 3, 1920x1080, front view" if args.n is None
+            "config": {"workload": ("C3: 3M synth_v1 Gaussians (seed 3), SH degree 3, 1920x1080, front view"
+                                    if args.gpus <= 1 else
+                                    "C4: same 3M-Gaussian scene, 256-view orbit (the CPU render of ONE view is timed, on "
+                                    "rank 0; views are independent and cost the same)") if args.n is None
                        else f"C3 scene with n={args.n}"},
             "cpu_baseline": b, "e2e": {"value": b["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0,
                                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
