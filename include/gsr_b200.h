@@ -63,7 +63,7 @@ typedef struct gsr_gaussians {
 /* Written by the device at the end of a frame (device memory; copy back when convenient). */
 typedef struct gsr_frame_info {
   uint32_t status;        /* gsr_status: GSR_ERR_DUP_OVERFLOW when n_dup exceeded max_dup (image is then invalid) */
-  uint32_t n_visible;     /* Gaussians that touch at least one tile */
+  uint32_t n_visible;     /* Gaussians the reference's loop blends (not culled, non-zero conic, non-empty tile rect; :441) */
   uint32_t n_dup;         /* (Gaussian, tile) pairs produced by binning */
   uint32_t reserved;
   uint64_t warp_evals;    /* Gaussian-pixel evaluations executed by blend, counted at warp granularity (x32) */

@@ -11,7 +11,7 @@
 // The digit histograms the one-sweep sorts need are by-products: those of the depth keys come from the preprocess
 // kernel, those of the tile ids from the emission (shared-memory counts, one flush per CTA) - no counting pass.
 // Stability of both sorts makes ties fall back to the Gaussian index, i.e. the result is bit-identical to a
-// stable CPU sort of the 64-bit keys (tests/test_gpu_binning.py checks exactly that).
+// stable CPU sort of the 64-bit keys (tests/test_gpu_parity.py::test_binning_equals_stable_sort_of_tile_depth_keys checks exactly that).
 // Replaces torch.sort at /root/reference/rasterize.py:424-425 and the implicit "for every Gaussian, for every
 // pixel of its bbox" visit order of :440-446.
 //
