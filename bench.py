@@ -328,7 +328,7 @@ def main():
         cam = cams[0]
         pre = R.preprocess(model, cam)
         binned = R.bin_tiles(pre, W, H, renderer.max_dup)
-        out = R.blend(pre, binned, W, H, count=True)
+        out = R.blend(pre, binned, W, H, count=True, track=False)
         torch.cuda.synchronize()
         cnt = out["info"].cpu().numpy().view(np.uint32)
         warp_evals = int(cnt[4]) | (int(cnt[5]) << 32)
@@ -338,12 +338,12 @@ def main():
         acc = np.zeros(3)
         reps = max(5, min(args.steps, 20))
         for _ in range(3):
-            pre = R.preprocess(model, cam); binned = R.bin_tiles(pre, W, H, renderer.max_dup); R.blend(pre, binned, W, H)
+            pre = R.preprocess(model, cam); binned = R.bin_tiles(pre, W, H, renderer.max_dup); R.blend(pre, binned, W, H, track=False)
         torch.cuda.synchronize()
         for _ in range(reps):
             evs[0].record(); pre = R.preprocess(model, cam)
             evs[1].record(); binned = R.bin_tiles(pre, W, H, renderer.max_dup)
-            evs[2].record(); R.blend(pre, binned, W, H)
+            evs[2].record(); R.blend(pre, binned, W, H, track=False)
             evs[3].record(); torch.cuda.synchronize()
             acc += [evs[k].elapsed_time(evs[k + 1]) for k in range(3)]
         t_pre, t_bin, t_blend = (acc / reps).tolist()

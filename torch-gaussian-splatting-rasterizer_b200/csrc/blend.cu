@@ -29,7 +29,7 @@ namespace gsr {
 
 constexpr float kParkedY = 1e18f;
 
-template <int PX, bool COUNT, bool RANKED>
+template <int PX, bool COUNT, bool RANKED, bool TRACK>
 __global__ void __launch_bounds__(256 / PX)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
@@ -170,7 +170,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
                   C1[k] = fmaf(wgt, gbl.x, C1[k]);
                   C2[k] = fmaf(wgt, gbl.y, C2[k]);
                   T[k] = fmaf(-alpha, T[k], T[k]);
-                  last[k] = (uint32_t)b * kBatch + j + u + 1;
+                  if (TRACK) last[k] = (uint32_t)b * kBatch + j + u + 1;  // only a later backward pass needs it
                   if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
                     fy[k] = kParkedY;
                     --live;
@@ -214,7 +214,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       image[p * 3 + 1] = C1[k];
       image[p * 3 + 2] = C2[k];
       if (final_T) final_T[p] = T[k];
-      if (n_contrib) n_contrib[p] = last[k];
+      if (TRACK && n_contrib) n_contrib[p] = last[k];
     }
   }
 }
@@ -267,16 +267,20 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   if (first_rank == 0 && last_rank == 0xFFFFFFFFu) blend_rank = nullptr;
   dim3 grid(tg.tiles_x, tile_row_end - tile_row_begin);
   const int px = blend_pixels_per_thread();
-#define GSR_BLEND_LAUNCH(PX, COUNT, RANKED)                                                                        \
-  blend_kernel<PX, COUNT, RANKED><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                                     \
+#define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
+  blend_kernel<PX, COUNT, RANKED, TRACK><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                              \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
       blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
+#define GSR_BLEND_PICK2(PX, COUNT, RANKED)                                                                         \
+  do {                                                                                                            \
+    if (n_contrib) GSR_BLEND_LAUNCH(PX, COUNT, RANKED, true); else GSR_BLEND_LAUNCH(PX, COUNT, RANKED, false);      \
+  } while (0)
 #define GSR_BLEND_PICK(PX)                                                          \
   do {                                                                              \
     if (blend_rank) {                                                               \
-      if (info_dev) GSR_BLEND_LAUNCH(PX, true, true); else GSR_BLEND_LAUNCH(PX, false, true);   \
+      if (info_dev) GSR_BLEND_PICK2(PX, true, true); else GSR_BLEND_PICK2(PX, false, true);   \
     } else {                                                                        \
-      if (info_dev) GSR_BLEND_LAUNCH(PX, true, false); else GSR_BLEND_LAUNCH(PX, false, false); \
+      if (info_dev) GSR_BLEND_PICK2(PX, true, false); else GSR_BLEND_PICK2(PX, false, false); \
     }                                                                               \
   } while (0)
   if (px == 8) GSR_BLEND_PICK(8); else if (px == 2) GSR_BLEND_PICK(2); else GSR_BLEND_PICK(4);

@@ -380,12 +380,13 @@ def bin_tiles(pre: Dict[str, torch.Tensor], width: int, height: int, max_dup: in
 
 
 def blend(pre, binned, width: int, height: int, count: bool = False, first_rank: int = 0, last_rank: int = U32_MAX,
-          tile_rows=None):
+          tile_rows=None, track: bool = True):
+    """``track=False`` omits ``n_contrib`` (only a backward pass needs it) - the instantiation a plain render uses."""
     _cabi.require_cuda()
     dev = pre["rec"].device
     image = torch.empty((height, width, 3), dtype=torch.float32, device=dev)
     final_T = torch.empty((height, width), dtype=torch.float32, device=dev)
-    n_contrib = torch.empty((height, width), dtype=torch.int32, device=dev)
+    n_contrib = torch.empty((height, width), dtype=torch.int32, device=dev) if track else None
     info = torch.zeros(8, dtype=torch.int32, device=dev) if count else None
     rb, re = (0, -1) if tile_rows is None else tile_rows
     _cabi.call("gsr_blend_fwd", _cabi.ptr(pre["rec"]), _cabi.ptr(binned["tile_gids"]), _cabi.ptr(binned["tile_ranges"]),
