@@ -26,7 +26,7 @@ __device__ __forceinline__ float blend_power(float A, float C, float B, float dx
 // around the threshold it is re-taken with the reference's own arithmetic.  Call only when power >= thr.
 __device__ __forceinline__ bool blend_alpha(float power, float opacity, float log2_opacity, float &alpha) {
   alpha = fminf(ex2_approx(fmaf(power, 1.4426950408889634f, log2_opacity)), kMaxDensity);
-  if (fabsf(fmaf(alpha, 255.0f, -1.0f)) < 1e-5f) alpha = fminf(fmul(opacity, expf(power)), kMaxDensity);
+  if (fabsf(alpha - kMinAlpha) < 3.9e-8f) alpha = fminf(fmul(opacity, expf(power)), kMaxDensity);  // 1e-5 relative
   return alpha > kMinAlpha && power <= 0.0f;  // :291
 }
 
