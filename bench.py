@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=3,
                     help="frames in flight per GPU: successive steps alternate between this many renderers/streams")
     args = ap.parse_args()
     if args.impl == "reference":

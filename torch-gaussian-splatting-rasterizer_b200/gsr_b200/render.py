@@ -282,7 +282,7 @@ def frame_lanes(count: int = 2, renderer: Optional[Renderer] = None):
 
 
 def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: Optional[Renderer] = None,
-                 out: Optional[torch.Tensor] = None, lanes: int = 2) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, lanes: int = 3) -> torch.Tensor:
     """Render a list of ``scenes.View`` with one resident model: ``[V,H,W,3]`` (video / orbit path).
 
     Frames are independent, so they are spread round-robin over `lanes` renderers/streams; the call returns with
