@@ -321,7 +321,7 @@ def main():
                        "l2_policy": "inputs (708 MB of Gaussian parameters) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"view-sharded x{world}" if world > 1 else "single GPU",
                        "frames_in_flight": n_streams},
-            "gpu_launches": 11 * args.steps, "frame_status": status_after}
+            "gpu_launches": 10 * args.steps, "frame_status": status_after}
 
     if rank == 0:
         # ---- per-stage timing with CUDA events on the launching stream (same kernels, stage entry points) ----

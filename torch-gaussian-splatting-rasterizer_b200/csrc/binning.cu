@@ -3,7 +3,8 @@
 // The textbook route sorts N_dup 64-bit (tile | depth) keys: ceil((32+log2 tiles)/8) = 6 radix passes over 12-byte
 // pairs.  The same total order - (tile, depth bits, Gaussian index) - is produced here with a third of the
 // traffic by sorting on the two fields separately, most significant last:
-//   1. stable sort of the N Gaussians by their 32-bit depth key (4 passes over 8-byte pairs, N << N_dup);
+//   1. stable sort of the Gaussians the reference's loop blends by their 32-bit depth key (4 passes over 8-byte
+//      pairs, N_vis << N_dup; the first pass reads the per-Gaussian keys directly and drops all the others);
 //   2. walk the Gaussians in depth order, warp-shuffle prefix scan of tiles-touched with a decoupled look-back
 //      across CTAs, and emit one (tile id, Gaussian id) pair per touched tile - pairs come out depth-ordered;
 //   3. stable sort of the pairs by tile id only (ceil(log2 tiles / 8) = 2 passes at 1080p);
@@ -45,85 +46,8 @@ struct BinCounters {   // device words shared by the binning kernels
   uint32_t n_dup;      // pairs actually stored (<= capacity): the n of the tile sort and of range marking
   uint32_t ticket;     // dynamic CTA index of scan_emit
   uint32_t n_vis;      // Gaussians the reference's loop blends = entries of the compacted depth sort
-  uint32_t compact_ticket;
+  uint32_t reserved;
 };
-
-// ---- ordered compaction of the blendable Gaussians --------------------------------------------------------------
-constexpr int kCompactThreads = 256;
-constexpr int kCompactItems = 8;
-constexpr int kCompactTile = kCompactThreads * kCompactItems;
-__global__ void __launch_bounds__(kCompactThreads)
-compact_kernel(int64_t n, const uint32_t *__restrict__ depth_key, const uint32_t *__restrict__ tiles_touched,
-               unsigned long long *status, uint32_t *ticket, uint32_t *__restrict__ vis_keys,
-               uint32_t *__restrict__ vis_gids, uint32_t *__restrict__ vis_count) {
-  __shared__ uint32_t s_warp[kCompactThreads / 32];
-  __shared__ uint32_t s_base, s_tile;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  // warp w owns items [w*256, w*256+256) of the tile, item j of lane l at j*32+l: coalesced, order = (warp, j, lane)
-  const int64_t base = (int64_t)tile * kCompactTile + warp * (kCompactItems * 32) + lane;
-  uint32_t votes[kCompactItems], mine = 0;
-#pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    const int64_t i = base + j * 32;
-    const bool keep = i < n && (__ldg(tiles_touched + i) >> 31);
-    votes[j] = __ballot_sync(0xFFFFFFFFu, keep);
-    mine += __popc(votes[j]);  // identical in every lane: the warp's count so far
-  }
-  if (lane == 0) s_warp[warp] = mine;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t total = 0;
-#pragma unroll
-    for (int w = 0; w < kCompactThreads / 32; ++w) total += s_warp[w];
-    unsigned long long prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u64(status, kScanInclusive | total);
-    } else {
-      if (lane == 0) st_volatile_u64(status + tile, kScanAggregate | total);
-      int64_t win = (int64_t)tile - 1;
-      while (true) {
-        const int64_t at = win - lane;
-        unsigned long long v = kScanInclusive;
-        if (at >= 0) {
-          v = ld_volatile_u64(status + at);
-          while ((v >> 62) == 0) {
-            __nanosleep(40);
-            v = ld_volatile_u64(status + at);
-          }
-        }
-        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v & kScanInclusive) != 0);
-        const int stop = incl ? __ffs(incl) - 1 : 32;
-        unsigned long long part = lane <= stop ? (v & kScanValue) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-        prefix += part;
-        if (incl) break;
-        win -= 32;
-      }
-      if (lane == 0) st_volatile_u64(status + tile, kScanInclusive | (prefix + total));
-    }
-    if (lane == 0) {
-      s_base = (uint32_t)prefix;
-      if ((int64_t)tile == (n + kCompactTile - 1) / kCompactTile - 1) *vis_count = (uint32_t)prefix + total;
-    }
-  }
-  __syncthreads();
-  uint32_t pos = s_base;
-  for (int w = 0; w < warp; ++w) pos += s_warp[w];
-#pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    if ((votes[j] >> lane) & 1u) {
-      const int64_t i = base + j * 32;
-      const uint32_t at = pos + __popc(votes[j] & ((1u << lane) - 1u));
-      vis_keys[at] = __ldg(depth_key + i);
-      vis_gids[at] = (uint32_t)i;
-    }
-    pos += __popc(votes[j]);
-  }
-}
 
 // Tile span of one Gaussian as the preprocess kernel stores it: x0 | y0 << 16, x1 | y1 << 16, keep mask (64 bits).
 // The number of pairs it stands for needs nothing else: the set bits of the mask for rects of <= 64 tiles (untested
@@ -369,7 +293,7 @@ tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, const BinCounters 
 }
 
 struct BinLayout {
-  size_t counters, scan_status, compact_status, tile_hist, depth_sort, tile_sort, vis_keys, vis_gids, order, dkeys_tmp,
+  size_t counters, scan_status, tile_hist, depth_sort, tile_sort, order, dkeys_tmp,
       dkeys_out, dvals_tmp, tkeys_a, tkeys_b, tkeys_c, tgids_a, tgids_b, total;
 };
 
@@ -384,12 +308,9 @@ static BinLayout bin_layout(int64_t n, int64_t max_dup) {
   const int64_t n1 = n > 0 ? n : 1, d1 = max_dup > 0 ? max_dup : 1;
   L.counters = take(sizeof(BinCounters));
   L.scan_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kScanTile));
-  L.compact_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kCompactTile));
   L.tile_hist = take(sizeof(uint32_t) * 4 * 256);
   L.depth_sort = take(sort_scratch_bytes(n1));
   L.tile_sort = take(sort_scratch_bytes(d1));
-  L.vis_keys = take(4 * (size_t)n1);
-  L.vis_gids = take(4 * (size_t)n1);
   L.order = take(4 * (size_t)n1);
   L.dkeys_tmp = take(4 * (size_t)n1);
   L.dkeys_out = take(4 * (size_t)n1);
@@ -442,21 +363,17 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   if (n == 0) return GSR_OK;
   if (!depth_order) depth_order = (uint32_t *)(ws + L.order);
 
-  // 0. ordered compaction: only the Gaussians the reference's loop blends (bit 31 of tiles_touched) need a depth
-  //    rank; packing their (depth key, index) pairs - still in index order, so the stable sort keeps breaking depth
-  //    ties by Gaussian index - lets the sort and the scan below skip the culled / off-screen ones.
+  // 1. depth order of the Gaussians the reference's loop blends (bit 31 of tiles_touched), ties by index.  The first
+  //    radix pass reads the per-Gaussian keys directly and drops everything else (a compaction for free: the sort
+  //    and the scan below never see the culled / off-screen ones); digit counts come from the preprocess kernel
+  //    when given.
   SortScratch s1, s2;
   int rc = sort_scratch_carve(ws + L.depth_sort, L.tile_sort - L.depth_sort, n, &s1);
   if (rc) return rc;
-  uint32_t *vis_keys = (uint32_t *)(ws + L.vis_keys), *vis_gids = (uint32_t *)(ws + L.vis_gids);
   uint32_t *vis_count = &ctr->n_vis;
-  compact_kernel<<<(unsigned)ceil_div64(n, kCompactTile), kCompactThreads, 0, stream>>>(
-      n, depth_key, tiles_touched, (unsigned long long *)(ws + L.compact_status), &ctr->compact_ticket, vis_keys, vis_gids,
-      vis_count);
-  GSR_LAUNCH_CHECK();
-  // 1. depth order of the blended Gaussians (ties by index); digit counts come from the preprocess kernel when given
-  rc = launch_sort_pairs(vis_keys, vis_gids, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
-                         (uint32_t *)(ws + L.dvals_tmp), n, vis_count, 0, 32, s1, stream, true, depth_hist);
+  rc = launch_sort_pairs(depth_key, nullptr, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
+                         (uint32_t *)(ws + L.dvals_tmp), n, vis_count, 0, 32, s1, stream, true, depth_hist, tiles_touched,
+                         vis_count);
   if (rc) return rc;
 
   // 2. prefix scan of the pair counts in depth order + pair emission + digit histograms of the tile ids
@@ -468,7 +385,7 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   GSR_LAUNCH_CHECK();
 
   // 3. stable sort of the pairs by tile id
-  rc = sort_scratch_carve(ws + L.tile_sort, L.vis_keys - L.tile_sort, max_dup, &s2);
+  rc = sort_scratch_carve(ws + L.tile_sort, L.order - L.tile_sort, max_dup, &s2);
   if (rc) return rc;
   uint32_t *sorted_tiles = (uint32_t *)(ws + L.tkeys_c);
   rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),

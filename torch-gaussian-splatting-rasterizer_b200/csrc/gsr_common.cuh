@@ -78,6 +78,6 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
-                      const uint32_t *ready_hist);
+                      const uint32_t *ready_hist, const uint32_t *live_flags = nullptr, uint32_t *n_live_out = nullptr);
 
 }  // namespace gsr

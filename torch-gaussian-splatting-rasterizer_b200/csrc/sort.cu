@@ -57,6 +57,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool live = true) {
 constexpr int kHistWarps = 8;
 __global__ void __launch_bounds__(kHistWarps * 32) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n_host,
                                                                      const uint32_t *__restrict__ n_dev,
+                                                                     const uint32_t *__restrict__ live_flags,
                                                                      uint32_t *__restrict__ hist, int begin_bit,
                                                                      int passes, uint32_t last_mask) {
   extern __shared__ uint32_t s_hist[];  // [kHistWarps][passes][kRadix]
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kHistWarps * 32) radix_hist_kernel(const uint3
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += stride) {
     const int64_t i = base + lane;
-    const bool live = i < n;
+    const bool live = i < n && (!live_flags || (__ldg(live_flags + i) >> 31));
     const uint32_t key = live ? __ldg(keys + i) : 0u;
     for (int p = 0; p < passes; ++p) {
       uint32_t d = (key >> (begin_bit + 8 * p)) & 255u;
@@ -119,12 +120,17 @@ __device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*
 constexpr int kBigThreads = 1024;
 constexpr int kBigWarps = kBigThreads / 32;
 
-template <int ITEMS>
+// FILTER: the first pass of a sort whose input still holds entries that must not take part (bit 31 of live_flags[i]
+// clear): they are ranked in a group of their own and never stored, so the pass also compacts - the separate
+// compaction kernel (and its look-back) of the binning stage is gone.  The pass then runs over all n_host entries and
+// writes the number of survivors (the sum of the digit counts) to *n_out for the passes that follow.
+template <int ITEMS, bool FILTER>
 __global__ void __launch_bounds__(kBigThreads, 1)
 onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
                 const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
-                uint32_t *ticket, int shift, uint32_t mask) {
+                uint32_t *ticket, int shift, uint32_t mask, const uint32_t *__restrict__ live_flags,
+                uint32_t *__restrict__ n_out) {
   constexpr int TILE = kBigThreads * ITEMS;
   extern __shared__ uint32_t s_dyn[];                      // s_keys[TILE] | s_vals[TILE]
   uint32_t *s_keys = s_dyn, *s_vals = s_dyn + TILE;
@@ -134,24 +140,26 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   __shared__ uint2 s_scan[kRadix / 32];
   __shared__ uint32_t s_part[4][kRadix];
   __shared__ uint32_t s_open[kRadix];
-  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_tile, s_live_total;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (int k = tid; k < kBigWarps * kRadix / 2; k += kBigThreads) reinterpret_cast<uint32_t *>(&s_hist[0][0])[k] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
-  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int64_t n = (!FILTER && n_dev) ? (int64_t)*n_dev : n_host;
   const int64_t num_tiles = (n + TILE - 1) / TILE;
   if ((int64_t)tile >= num_tiles) return;
 
   // ---- load: warp w owns the contiguous run [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item i of lane l at i*32+l ----
   const int64_t base = (int64_t)tile * TILE + warp * (ITEMS * 32) + lane;
   uint32_t key[ITEMS];
+  uint32_t live_mask = 0xFFFFFFFFu;  // FILTER: bit i = item i takes part
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = base + i * 32;
     key[i] = idx < n ? __ldg(keys_in + idx) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
+    if (FILTER && !(idx < n && (__ldg(live_flags + idx) >> 31))) live_mask &= ~(1u << i);
   }
 
   // ---- rank inside the warp, in (item, lane) order ----
@@ -159,13 +167,14 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t peers = match_digit(d);
+    const bool live = !FILTER || ((live_mask >> i) & 1u);
+    const uint32_t peers = FILTER ? match_digit(d, live) : match_digit(d);
     const int leader = __ffs(peers) - 1;
     uint32_t before = 0;
-    if (lane == leader) before = s_hist[warp][d];
+    if (lane == leader && live) before = s_hist[warp][d];
     before = __shfl_sync(0xFFFFFFFFu, before, leader);
     rank[i] = (uint16_t)(before + __popc(peers & ((1u << lane) - 1u)));
-    if (lane == leader) s_hist[warp][d] = (uint16_t)(before + __popc(peers));
+    if (lane == leader && live) s_hist[warp][d] = (uint16_t)(before + __popc(peers));
     __syncwarp();
   }
   __syncthreads();
@@ -181,6 +190,10 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
   }
   const uint2 ex = block_exclusive_scan2(make_uint2(count, tid < kRadix ? __ldg(hist + tid) : 0u), s_scan);
+  if (FILTER && tid == kRadix - 1) {
+    s_live_total = ex.x + count;                                      // survivors of this tile
+    if (tile == 0) *n_out = ex.y + __ldg(hist + tid);                 // survivors of the whole input
+  }
 
   // ---- decoupled look-back, 32 predecessor tiles per round trip: the four quarters of the CTA each fetch 8
   //      predecessors of digit d with independent, coalesced loads and fold them in order up to the first inclusive
@@ -248,7 +261,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
     const uint32_t pos = s_excl[d] + s_hist[warp][d] + rank[i];
-    s_keys[pos] = key[i];
+    if (!FILTER || ((live_mask >> i) & 1u)) s_keys[pos] = key[i];
     rank[i] = (uint16_t)pos;  // TILE <= 24576 fits
   }
   {
@@ -259,12 +272,13 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
       val[i] = idx < n ? (vals_in ? __ldg(vals_in + idx) : (uint32_t)idx) : 0u;
     }
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) s_vals[rank[i]] = val[i];
+    for (int i = 0; i < ITEMS; ++i)
+      if (!FILTER || ((live_mask >> i) & 1u)) s_vals[rank[i]] = val[i];
   }
   __syncthreads();
   // ---- runs of equal digits leave coalesced ----
   const int64_t remaining = n - (int64_t)tile * TILE;
-  const int valid = remaining < TILE ? (int)remaining : TILE;
+  const int valid = FILTER ? (int)s_live_total : (remaining < TILE ? (int)remaining : TILE);
   for (int j = tid; j < valid; j += kBigThreads) {
     const uint32_t k = s_keys[j];
     const uint32_t dst = s_gbase[(k >> shift) & mask] + j;
@@ -314,8 +328,10 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
-                      const uint32_t *ready_hist) {
+                      const uint32_t *ready_hist, const uint32_t *live_flags, uint32_t *n_live_out) {
   GSR_REQUIRE(n >= 0 && n < (1ll << 30), "sort size out of range (must be < 2^30)");
+  GSR_REQUIRE((live_flags == nullptr) == (n_live_out == nullptr), "live_flags and n_live_out go together");
+  GSR_REQUIRE(!live_flags || n_dev == n_live_out, "a filtering sort counts its own survivors: n_dev must be n_live_out");
   GSR_REQUIRE(begin_bit >= 0 && end_bit <= 32 && end_bit > begin_bit, "bad bit range");
   GSR_REQUIRE(keys_in && keys_out && values_out && keys_tmp && values_tmp, "null sort buffer");
   if (n == 0) return GSR_OK;
@@ -338,7 +354,8 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     int64_t want = ceil_div64(n, 256 * 16);
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
     const size_t smem = sizeof(uint32_t) * kHistWarps * passes * kRadix;
-    radix_hist_kernel<<<blocks, kHistWarps * 32, smem, stream>>>(keys_in, n, n_dev, s.hist, begin_bit, passes, last_mask);
+    radix_hist_kernel<<<blocks, kHistWarps * 32, smem, stream>>>(keys_in, n, live_flags ? nullptr : n_dev, live_flags, s.hist,
+                                                                 begin_bit, passes, last_mask);
     GSR_LAUNCH_CHECK();
   }
   const uint32_t *kin = keys_in, *vin = values_in;
@@ -349,18 +366,22 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     if (p == passes - 1 && skip_final_keys) kout = nullptr;  // caller only wants the permutation
     const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
     const size_t smem = sizeof(uint32_t) * 2 * (size_t)kBigThreads * items;
-#define GSR_SWEEP(IT)                                                                                             \
-  case IT: {                                                                                                      \
+    const bool filter = p == 0 && live_flags != nullptr;
+#define GSR_SWEEP_LAUNCH(IT, F)                                                                                   \
+  do {                                                                                                            \
     static bool configured = false;                                                                               \
     if (!configured) {                                                                                            \
-      GSR_CHECK_CUDA(cudaFuncSetAttribute(onesweep_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+      GSR_CHECK_CUDA(cudaFuncSetAttribute(onesweep_kernel<IT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                           (int)(sizeof(uint32_t) * 2 * kBigThreads * IT)));                        \
       configured = true;                                                                                          \
     }                                                                                                             \
-    onesweep_kernel<IT><<<(unsigned)tiles, kBigThreads, smem, stream>>>(kin, vin, kout, vout, n, n_dev,            \
-                                                                        hist + p * kRadix,                        \
-                                                                        s.status + p * s.status_stride,           \
-                                                                        s.tickets + p, begin_bit + 8 * p, mask);   \
+    onesweep_kernel<IT, F><<<(unsigned)tiles, kBigThreads, smem, stream>>>(                                        \
+        kin, vin, kout, vout, n, n_dev, hist + p * kRadix, s.status + p * s.status_stride, s.tickets + p,          \
+        begin_bit + 8 * p, mask, live_flags, n_live_out);                                                         \
+  } while (0)
+#define GSR_SWEEP(IT)                                                                                             \
+  case IT: {                                                                                                      \
+    if (filter) GSR_SWEEP_LAUNCH(IT, true); else GSR_SWEEP_LAUNCH(IT, false);                                     \
   } break;
     switch (items) {
       GSR_SWEEP(4)
@@ -371,6 +392,7 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
       GSR_SWEEP(24)
     }
 #undef GSR_SWEEP
+#undef GSR_SWEEP_LAUNCH
     GSR_LAUNCH_CHECK();
     kin = kout;
     vin = vout;
@@ -396,5 +418,5 @@ extern "C" int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in
   int rc = sort_scratch_carve(workspace, workspace_bytes, n, &s);
   if (rc) return rc;
   return launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, n_dev, begin_bit,
-                           end_bit, s, (cudaStream_t)stream, false, nullptr);
+                           end_bit, s, (cudaStream_t)stream, false, nullptr, nullptr, nullptr);
 }
