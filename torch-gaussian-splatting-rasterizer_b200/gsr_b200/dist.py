@@ -112,6 +112,9 @@ class PeerGather:
         self.buf = symm.empty(shape, dtype=torch.float32, device=device)
         self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.peers = [self.handle.get_buffer(p, shape, torch.float32) for p in range(self.world)]
+        # one DMA stream per few destinations: a single copy stream serialises the world-size copies of a frame on one
+        # copy engine (8 x 25 MB took about as long as a frame renders); several streams keep more engines / links busy
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(min(4, max(1, self.world - 1)))]
 
     @staticmethod
     def create(frame_shape: Sequence[int], device, slots: int = 2, group=None) -> Optional["PeerGather"]:
@@ -127,9 +130,17 @@ class PeerGather:
             return None
 
     def push(self, frame: torch.Tensor, slot: int) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)  # the frame is complete (and the slot free) at this point of the caller's stream
+        for st in self.copy_streams:
+            st.wait_event(ready)
         for k in range(self.world):  # staggered so that the ranks do not all write to the same peer at once
             p = (self.rank + k) % self.world
-            self.peers[p][slot, self.rank].copy_(frame, non_blocking=True)
+            with torch.cuda.stream(self.copy_streams[k % len(self.copy_streams)]):
+                self.peers[p][slot, self.rank].copy_(frame, non_blocking=True)
+        for st in self.copy_streams:
+            cur.wait_stream(st)
         self.handle.barrier(channel=slot)
         return self.buf[slot]
 
