@@ -73,3 +73,11 @@ def _worker(rank, world, port, n_views, H, W):
 @pytest.mark.parametrize("n_views,H,W", [(5, 40, 24), (4, 33, 16)])
 def test_two_rank_gloo_gathers(n_views, H, W):
     mp.spawn(_worker, args=(2, _free_port(), n_views, H, W), nprocs=2, join=True)
+
+
+def test_peer_gather_declines_without_nccl_cuda():
+    """PeerGather is the CUDA / NCCL fast path; on CPU (or without a process group) `create` returns None and the
+    callers use the collective - the path the gloo tests above exercise."""
+    from gsr_b200 import dist as gd
+
+    assert gd.PeerGather.create((4, 4, 3), "cpu") is None
