@@ -130,3 +130,26 @@ def test_scene_io_round_trip(tmp_path):
     sh = utils.read_color_components(ply)
     assert tuple(sh.shape) == (257, 16, 3) and sh.stride() == (1, 257, 16 * 257)
     assert np.array_equal(sh.numpy(), cloud.sh_planar().transpose(2, 1, 0))
+
+
+def test_ground_truth_comparison_and_frame_writer_run_on_the_host(tmp_path):
+    """The helpers around the path are plain host code: PSNR / side-by-side PNG against a photo and
+    the frame-sequence writer need neither the library nor a GPU."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    import rasterize
+
+    rng = np.random.default_rng(0)
+    a = torch.from_numpy(rng.random((20, 30, 3), dtype=np.float32))
+    b = (a + 0.01).clamp(0, 1)
+    assert rasterize.psnr(a, a) == float("inf")
+    assert 35.0 < rasterize.psnr(a, b) < 45.0  # an offset of 0.01 is 40 dB
+    gt = tmp_path / "gt.png"
+    Image.fromarray((b.numpy() * 255).astype(np.uint8)).save(gt)
+    out = rasterize.compare_with_ground_truth(a, str(gt), str(tmp_path / "cmp.png"))
+    assert out["psnr_db"] > 30 and out["mae"] < 0.02
+    assert Image.open(tmp_path / "cmp.png").size == (30, 40)  # render above the photo
+    n = rasterize.write_frame_sequence(torch.stack([a, b]), str(tmp_path / "seq"))
+    assert n == 2 and sorted(p.name for p in (tmp_path / "seq").iterdir()) == ["frame_0000000.png", "frame_0000001.png"]
