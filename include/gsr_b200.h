@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 #define GSR_TILE 16 /* BLOCK_SIZE, rasterize.py:34 */
 
 typedef enum gsr_status {
@@ -60,12 +60,16 @@ typedef struct gsr_gaussians {
   const float *sh;            int64_t sh_sn, sh_sk, sh_sc;  /* [n,16,3] utils.py:21-31 (planar [3,16,n] view is the fast layout) */
 } gsr_gaussians;
 
-/* Written by the device at the end of a frame (device memory; copy back when convenient). */
+/* Written by the device at the end of a frame (device memory; copy back when convenient).  The caller zeroes it
+ * once.  `status` and `n_dup_peak` are STICKY: no entry point ever clears them, so one read-back after a whole
+ * sequence of frames (an orbit, a batch of views) still sees an overflow that happened on any of them, and
+ * `n_dup_peak` says which capacity would have sufficed.  The caller clears them after handling the error.
+ * `n_visible` / `n_dup` describe the LAST frame; `warp_evals` / `pixel_evals` accumulate (gsr_blend_fwd only). */
 typedef struct gsr_frame_info {
-  uint32_t status;        /* gsr_status: GSR_ERR_DUP_OVERFLOW when n_dup exceeded max_dup (image is then invalid) */
+  uint32_t status;        /* STICKY gsr_status: GSR_ERR_DUP_OVERFLOW when n_dup exceeded max_dup (that frame's image is invalid) */
   uint32_t n_visible;     /* Gaussians the reference's loop blends (not culled, non-zero conic, non-empty tile rect; :441) */
-  uint32_t n_dup;         /* (Gaussian, tile) pairs produced by binning */
-  uint32_t reserved;
+  uint32_t n_dup;         /* (Gaussian, tile) pairs the last frame needed (may exceed max_dup) */
+  uint32_t n_dup_peak;    /* STICKY maximum of n_dup over the frames since the caller last cleared it */
   uint64_t warp_evals;    /* Gaussian-pixel evaluations executed by blend, counted at warp granularity (x32) */
   uint64_t pixel_evals;   /* evaluations executed by pixels that had not yet terminated */
 } gsr_frame_info;
@@ -91,13 +95,46 @@ int gsr_fp32_fma_peak(double *tflops, double *sm_mhz_effective);
  * first_rank/last_rank restrict blending to Gaussians whose global depth rank r satisfies
  * first_rank <= r < last_rank (progressive renders, :448-452); pass 0 and UINT32_MAX for everything.
  * tile_row_begin/end restrict the frame to a band of tile rows (multi-GPU band sharding); rows outside
- * the band are left untouched in image.  info_dev (device, may be NULL) receives counters.
+ * the band are left untouched in image.  info_dev (device, may be NULL) receives counters; it is never cleared by
+ * the library (see gsr_frame_info).  Workspace offsets of everything gsr_render_bwd replays do not depend on max_dup.
  * --------------------------------------------------------------------------------------------- */
 int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);
 int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
                    size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
                    uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
                    gsr_frame_info *info_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Prepared model: the view-independent half of the per-Gaussian set-up, computed once per model.
+ * Sigma = R S S^T R^T (:97-120), sigmoid(opacity) (:358) and the two logarithms of the blend record do not depend on
+ * the camera; gsr_prepare evaluates them with the same device functions (same operation order, bit-identical results)
+ * the per-view kernel of gsr_preprocess_fwd uses, and stores them with xyz and the SH coefficients in blocks of
+ * 32 Gaussians whose rows are 32 x 16 bytes:
+ *     geometry [blocks][3][32][4] f32 :  x y z opacity | S00 S01 S02 S11 | S12 S22 thr log2(opacity)
+ *     SH       [blocks][12][32][4] f32:  row 4c + j = coefficients 4j .. 4j+3 of colour channel c
+ * (geometry first, SH at the next 256-byte boundary; 240 B per Gaussian).  `prepared` must be 256-byte aligned and
+ * gsr_prepared_bytes(n) large.  A resident scene (video / orbit / serving) is prepared once and rendered with
+ * gsr_render_prepared_fwd / gsr_render_views_fwd; whoever changes a parameter calls gsr_prepare again.
+ * --------------------------------------------------------------------------------------------- */
+int gsr_prepared_bytes(int64_t n, size_t *bytes);
+int gsr_prepare(const gsr_gaussians *g, void *prepared, size_t prepared_bytes, void *stream);
+/* gsr_preprocess_fwd over a prepared model (no debug outputs; depth_hist is mandatory).  Bit-identical outputs. */
+int gsr_preprocess_prepared_fwd(const void *prepared, int64_t n, const gsr_camera *cam, int32_t tile_row_begin,
+                                int32_t tile_row_end, uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span,
+                                float *rec, uint32_t *depth_hist, void *stream);
+/* gsr_render_fwd over a prepared model (same workspace, same outputs, bit-identical image). */
+int gsr_render_prepared_fwd(const void *prepared, int64_t n, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                            size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                            uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                            gsr_frame_info *info_dev, void *stream);
+/* A batch of views of one prepared model (the 256-view orbit of :448-466's video path, a serving batch): view v is
+ * enqueued on streams[v % n_lanes] using workspaces[v % n_lanes] (each workspace_bytes large) and info_dev[v % n_lanes];
+ * images + v * image_stride_floats receives frame v.  cams_host is a HOST array of n_views cameras (all the same image
+ * size).  Nothing synchronises: the caller joins the streams, then reads info_dev[0..n_lanes) (status is sticky, so one
+ * read-back covers every frame of the lane). */
+int gsr_render_views_fwd(const void *prepared, int64_t n, const gsr_camera *cams_host, int32_t n_views, int64_t max_dup,
+                         void *const *workspaces, size_t workspace_bytes, int32_t n_lanes, void *const *streams,
+                         float *images, int64_t image_stride_floats, gsr_frame_info *info_dev);
 
 /* Same frame with HOST buffers: uploads the parameters, renders, downloads the image, synchronises.
  * This is the call that stands where the reference's run_rasterization body stands (:354-452). */

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_struct_sizes(lib):
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
     assert ctypes.sizeof(camera.CameraStruct) == 4 * (16 + 16 + 3 + 2 + 2) + 16
     assert ctypes.sizeof(_cabi.Gaussians) == 8 * 16
     assert ctypes.sizeof(_cabi.FrameInfo) == 32

@@ -25,17 +25,33 @@ def _cuda_grads(cloud, cam, grad_image):
                                             d_sh=sh.grad)
 
 
-def _check(got, want, rtol):
-    """Entries agree to rtol of the tensor's largest gradient.  The keep test alpha > 1/255 is discontinuous: one
-    pixel whose decision flips between two float implementations moves that Gaussian's gradient by a finite amount
-    (d alpha / d opacity = exp(power) is large for faint Gaussians), so a handful of entries (2, or 0.5 %) may deviate,
-    by at most 2 % of the scale."""
+def _check(got, want, rtol, label, allow=0, worst=None):
+    """EVERY entry agrees to rtol of the tensor's largest gradient, unless `allow` says otherwise.  The keep test
+    alpha > 1/255 is discontinuous: a pixel whose decision flips between two float implementations moves that Gaussian's
+    gradient by a finite amount, so a case may name the number of entries it tolerates above rtol (`allow`) and how far
+    (`worst`, fraction of the scale) - the numbers measured on the B200 are recorded in gpurun_out/grad_deviation.json."""
+    import json
+    import os
+
+    stats = {}
     for k in KEYS:
         g, w = got[k].cpu().numpy(), np.asarray(want[k])
         scale = max(float(np.abs(w).max()), 1e-6)
         err = np.abs(g - w)
-        assert int((err > rtol * scale).sum()) <= max(2, int(5e-3 * err.size)), (k, float(err.max()), scale)
-        assert float(err.max()) <= 2e-2 * scale, (k, float(err.max()), scale)
+        stats[k] = dict(entries=int(err.size), over_rtol=int((err > rtol * scale).sum()), max_err_over_scale=float(err.max() / scale))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "grad_deviation.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    rows = {}
+    if os.path.exists(path):
+        with open(path) as fh:
+            rows = json.load(fh)
+    rows[label] = dict(rtol=rtol, **stats)
+    with open(path, "w") as fh:
+        json.dump(rows, fh, indent=1)
+    for k, st in stats.items():
+        assert st["over_rtol"] <= allow, (label, k, st)
+        assert st["max_err_over_scale"] <= (worst if worst is not None else rtol), (label, k, st)
 
 
 def test_gradients_match_autograd_through_the_reference(golden):
@@ -45,7 +61,7 @@ def test_gradients_match_autograd_through_the_reference(golden):
     cam = camera.camera_for(intr, view, GRAD_CASE["degree"])
     img, grads = _cuda_grads(cloud, cam, g["grad_image"])
     assert np.abs(img - g["image"]).max() < 2e-4
-    _check(grads, g, rtol=2e-3)
+    _check(grads, g, rtol=2e-3, label="reference_autograd_n48")
 
 
 @pytest.mark.parametrize("n,seed,scale,w,h,degree,qvec,tvec", [
@@ -62,7 +78,37 @@ def test_gradients_match_autograd_through_the_port(n, seed, scale, w, h, degree,
     want = torch_port.gradients(cloud, cam, G)
     img, grads = _cuda_grads(cloud, cam, G)
     assert np.abs(img - want["image"]).max() < 2e-4
-    _check(grads, want, rtol=3e-3)
+    _check(grads, want, rtol=3e-3, label=f"port_n{n}_seed{seed}")
+
+
+def test_gradients_of_a_scene_larger_than_the_default_capacity():
+    """N > 8192: the renderer tightens its pair capacity after the checked forward frame, so forward and backward are
+    called with different max_dup.  Workspace offsets of what the backward replays must not depend on it
+    (tile ranges were read from inside the gid array).  Checked against autograd through the torch port and
+    against a renderer whose capacity never changes."""
+    from gsr_b200 import render as R
+
+    n, w, h = 12_000, 96, 64
+    cloud = scenes.synth_v1(n, 61, scale_factor=0.35)
+    cloud.xyz[:, 0] *= 3.0   # two thirds of the cloud off screen: keeps the per-Gaussian CPU loop of the port short
+    intr = scenes.Intrinsics.synthetic(w, h)
+    cam = camera.camera_for(intr, scenes.front_view(0), 3)
+    G = np.random.default_rng(5).uniform(-1, 1, (h, w, 3)).astype(np.float32)
+    img, grads = _cuda_grads(cloud, cam, G)
+    # same frame with a fixed capacity
+    model = R.GaussianModel.from_cloud(cloud)
+    fixed = R.Renderer(); fixed.adaptive_capacity = False
+    leaves = [t.clone().requires_grad_(True) for t in (model.xyz, model.log_scales, model.rots, model.opacity)]
+    sh = model.sh.contiguous().clone().requires_grad_(True)
+    (R.render_differentiable(*leaves, sh, cam, renderer=fixed) * torch.from_numpy(G).cuda()).sum().backward()
+    for k, t in zip(KEYS, leaves + [sh]):
+        assert torch.equal(grads[k], t.grad), k
+    tight = R.Renderer()
+    tight.render(model, cam)
+    assert tight.max_dup < max(int(tight.dup_factor * n), 1 << 16)  # the tightening really happened
+    want = torch_port.gradients(cloud, cam, G)
+    assert np.abs(img - want["image"]).max() < 2e-4
+    _check(grads, want, rtol=3e-3, label="port_n12000")
 
 
 def test_band_gradients_sum_to_the_full_gradient():

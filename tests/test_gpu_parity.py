@@ -291,6 +291,168 @@ def test_sh_and_staged_helpers_match_reference(golden, R):
     assert torch.equal(Rm, camera.rotation_from_quaternion(torch.from_numpy(cloud.rots.T.copy())))
 
 
+def test_quaternion_and_covariance_drop_ins_match_reference_goldens(golden, tmp_path):
+    """rasterize.quaternion_to_rotation_matrix and get_covariance_matrix_from_mesh against vectors produced by the
+    unmodified reference (tests/golden/make_helper_golden.py): the former is pure +,-,* arithmetic => bit-exact; the
+    latter goes through exp(scale), where torch's MKL exp differs from the correctly rounded value on ~1 % of inputs
+    by one ulp => 2e-6 relative, and bit-exact against the oracle."""
+    import rasterize
+    from gsr_b200.ply import PlyData, write_gaussian_ply
+
+    g = golden("helpers")
+    Rm = rasterize.quaternion_to_rotation_matrix(torch.from_numpy(g["quat"]).cuda())
+    assert Rm.is_cuda and tuple(Rm.shape) == (3, 3, 512) and Rm.dtype == torch.float32
+    assert np.array_equal(_bits(Rm.cpu().numpy()), _bits(g["rotmat"]))
+    # host route (a handful of float64 camera quaternions) follows the same formula
+    q64 = torch.from_numpy(g["quat"][:, :8].astype(np.float64))
+    assert np.allclose(rasterize.quaternion_to_rotation_matrix(q64).numpy(), g["rotmat"][:, :, :8], rtol=1e-6, atol=1e-30)
+    cloud = scenes.synth_v1(700, 31, scale_factor=0.7)
+    cloud.rots[:3] = 0.0
+    path = str(tmp_path / "p.ply")
+    write_gaussian_ply(path, cloud.ply_table())
+    cov = rasterize.get_covariance_matrix_from_mesh(PlyData.read(path))
+    assert cov.is_cuda and tuple(cov.shape) == (700, 3, 3)
+    cov = cov.cpu().numpy()
+    scale = np.abs(g["cov3d"]).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(cov - g["cov3d"]) <= 2e-6 * scale + 1e-30).all()
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(64, 48), scenes.front_view(0), 3)
+    assert np.array_equal(_bits(cov), _bits(c_oracle.preprocess(cloud, cam)["cov3d"]))
+
+
+@pytest.mark.parametrize("name", NAMES + ["big_deg0", "big_deg1", "big_deg2", "big_deg3"])
+def test_prepared_preprocess_is_bit_identical(name, R):
+    """The resident-scene path (gsr_prepare once per model + the per-view kernel over the blocked layout) must produce
+    exactly what the fused raw-parameter kernel produces: every output word, every SH degree, ragged last block."""
+    if name.startswith("big"):
+        degree = int(name[-1])
+        cloud = scenes.synth_v1(100_003, 5 + degree, scale_factor=0.25)   # not a multiple of 32
+        intr = scenes.Intrinsics.synthetic(640, 360)
+        cam = camera.camera_for(intr, scenes.orbit_views(1, total=11, first=2 + degree)[0], degree)
+    else:
+        cloud, intr, view, cam = _case(name)
+    model = R.GaussianModel.from_cloud(cloud)
+    a = R.preprocess(model, cam)
+    b = R.preprocess(model, cam, prepared=True)
+    tt = a["tiles_touched"]
+    assert torch.equal(a["depth_key"], b["depth_key"])
+    assert torch.equal(tt, b["tiles_touched"])
+    assert torch.equal(a["tile_span"], b["tile_span"])
+    assert torch.equal(a["depth_hist"], b["depth_hist"])
+    vis = (tt & 0x7FFFFFFF) != 0                       # records are written for Gaussians that keep a tile
+    assert torch.equal(a["rec"][vis].view(torch.int32), b["rec"][vis].view(torch.int32))
+    assert int(vis.sum()) > 0
+    # band mode goes through the same body
+    rows = (1, 3)
+    a2, b2 = R.preprocess(model, cam, tile_rows=rows), R.preprocess(model, cam, tile_rows=rows, prepared=True)
+    assert torch.equal(a2["tile_span"], b2["tile_span"]) and torch.equal(a2["tiles_touched"], b2["tiles_touched"])
+    # whole frames: bit-identical images, and the strided (interleaved SH) input prepares to the same model
+    r = R.Renderer()
+    img_p, img_r = r.render(model, cam, prepared=True).clone(), r.render(model, cam, prepared=False)
+    assert torch.equal(img_p, img_r)
+    sh_i = model.sh.contiguous()                       # [N,16,3] interleaved
+    m2 = R.GaussianModel(model.xyz, model.log_scales, model.rots, model.opacity, sh_i)
+    assert m2.sh.stride() != model.sh.stride() and torch.equal(m2.prepare(), model.prepare())
+
+
+def test_generate_video_cli_branch(tmp_path):
+    """`--generate_video` (reference :427-429, :448-466): a PNG after blended Gaussian 1, 1001, 2001, ... named by the
+    iteration step, then 40 copies of the LAST SNAPSHOT named n_blended + 1000 i + 1; the snapshots are the oracle's
+    image after exactly that many blended Gaussians."""
+    import os
+
+    from PIL import Image
+
+    import rasterize
+
+    cloud = scenes.synth_v1(2600, 71, scale_factor=0.6)
+    intr = scenes.Intrinsics.synthetic(96, 64)
+    view = scenes.front_view(0)
+    root = scenes.write_scene_dir(str(tmp_path / "scene"), cloud, intr, [view])
+    out = str(tmp_path / "out")
+    rasterize.run_rasterization.callback(input_dir=root, trained_model_path=root, output_path=out, scene_index=0,
+                                         scale_factor=2, generate_video=True)
+    cam = camera.camera_for(intr, view, 3)
+    o = c_oracle.render(cloud, cam)
+    n_blend = int(o["n_blended"])
+    assert n_blend > 2000, n_blend  # at least three snapshots
+    snaps = list(range(0, n_blend, 1000))
+    tail = [n_blend + 1000 * i + 1 for i in range(1, 41)]
+    want = sorted(f"image_iter_{str(k).zfill(7)}.png" for k in snaps + tail)
+    assert sorted(os.listdir(os.path.join(out, "images"))) == want
+    blended_pos = np.nonzero(o["skip"][o["order"]] == 0)[0]
+
+    def load(k):
+        return np.asarray(Image.open(os.path.join(out, "images", f"image_iter_{str(k).zfill(7)}.png")), dtype=np.int32)
+
+    for k in (snaps[0], snaps[-1]):
+        ref, _, nb = c_oracle.blend(o, o["order"], cam.width, cam.height, 0, int(blended_pos[k]) + 1)
+        assert nb == k + 1
+        want_png = (np.clip(ref, 0, 1) * 255.0).astype(np.uint8).astype(np.int32)
+        assert np.abs(load(k) - want_png).max() <= 1  # uint8 truncation of values that agree to 2e-4
+    assert np.array_equal(load(tail[0]), load(snaps[-1])) and np.array_equal(load(tail[-1]), load(snaps[-1]))
+    assert os.path.exists(os.path.join(out, "render.png"))
+
+
+def test_sticky_overflow_status_across_frames(R):
+    """A pair-capacity overflow on ANY frame of an unchecked sequence is still visible afterwards (device-side sticky
+    status + peak need), and render_views redraws the batch with a sufficient capacity."""
+    cloud = scenes.synth_v1(60_000, 13, scale_factor=0.3)
+    intr = scenes.Intrinsics.synthetic(400, 240)
+    views = scenes.orbit_views(4, total=16)
+    cams = [camera.camera_for(intr, v, 3) for v in views]
+    model = R.GaussianModel.from_cloud(cloud)
+    want = [R.Renderer().render(model, c).clone() for c in cams]
+    need = []
+    for c in cams:
+        rr = R.Renderer(); rr.render(model, c); need.append(rr.frame_info()["n_dup"])
+    r = R.Renderer()
+    r.adaptive_capacity = False
+    worst = int(np.argmax(need))
+    r.reserve(model.n, intr.width, intr.height, max_dup=max(need) - 10)   # only the worst view overflows
+    order = [worst] + [i for i in range(4) if i != worst]                   # ... and it is NOT the last frame
+    if sorted(need)[-2] > max(need) - 10:
+        pytest.skip("two views need the same capacity")
+    for i in order:
+        r.render(model, cams[i], check=False)
+    info = r.frame_info()
+    assert info["status"] == 4 and info["n_dup_peak"] == max(need) and info["n_dup"] == need[order[-1]]
+    with pytest.raises(Exception):
+        r.check_status()
+    assert r.max_dup >= max(need) and r.frame_info()["status"] == 0        # capacity raised, status cleared
+    # render_views: one lane starts with too small a capacity; the result is still right
+    lanes = R.frame_lanes(2, r)
+    for rend, _ in lanes:
+        rend.adaptive_capacity = False
+        rend.reserve(model.n, intr.width, intr.height, max_dup=max(need) - 10)
+    frames = R.render_views(model, intr, views, 3, renderer=r, lanes=2)
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(frames[i], want[i])
+    # the C-level batch entry point does the same through one foreign call
+    br = R.BatchRenderer(lanes=2)
+    br.reserve(model.n, intr.width, intr.height, max_dup=max(need) - 10)
+    frames = br.render(model, cams)
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(frames[i], want[i])
+    assert br.max_dup >= max(need)
+
+
+def test_one_process_two_devices(R):
+    """Per-device (not process-wide) kernel attributes and SM-count caches: the same process renders on cuda:1 after
+    cuda:0, including the > 48 KB dynamic shared memory kernels (one-sweep sort, PLY unpack)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cloud = scenes.synth_v1(300_000, 3, scale_factor=0.25)
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(640, 400), scenes.front_view(0), 3)
+    imgs = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            model = R.GaussianModel.from_cloud(cloud, device=f"cuda:{dev}")
+            imgs.append(R.Renderer(device=f"cuda:{dev}").render(model, cam).cpu())
+    assert torch.equal(imgs[0], imgs[1])
+
+
 def test_rasterize_gaussian_loop_matches_reference(golden):
     """The reference's own loop (rasterize.py:436-446) written against the drop-in rasterize_gaussian."""
     import rasterize

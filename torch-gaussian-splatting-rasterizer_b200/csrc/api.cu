@@ -16,9 +16,13 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+// One frame's workspace.  Offsets of everything a backward pass replays (tiles_touched, rec, tile_ranges, tile_gids)
+// depend on n and the image size only - NOT on max_dup - so a forward and its backward agree on them whatever pair
+// capacity each was called with; buffers whose SIZE depends on max_dup come last.  The zero-initialised buffers are
+// two contiguous runs: depth_hist | tile_ranges, and the head of the binning workspace.
 struct FrameLayout {
-  size_t depth_key, depth_hist, tiles_touched, tile_span, rec, order, blend_rank, tile_gids, tile_ranges, bin, total;
-  size_t bin_bytes;
+  size_t depth_key, tiles_touched, tile_span, rec, order, blend_rank, depth_hist, tile_ranges, tile_gids, bin, total;
+  size_t bin_bytes, zero_a_bytes, zero_b_bytes;
 };
 
 static int frame_layout(int64_t n, int width, int height, int64_t max_dup, FrameLayout *L) {
@@ -31,17 +35,19 @@ static int frame_layout(int64_t n, int width, int height, int64_t max_dup, Frame
   const size_t n1 = (size_t)(n > 0 ? n : 1), d1 = (size_t)(max_dup > 0 ? max_dup : 1);
   const TileGrid tg = make_grid(width, height);
   L->depth_key = take(4 * n1);
-  L->depth_hist = take(4 * 1024);
   L->tiles_touched = take(4 * n1);
   L->tile_span = take(16 * n1);
   L->rec = take(sizeof(float) * GSR_REC_FLOATS * n1);
   L->order = take(4 * n1);
   L->blend_rank = take(4 * n1);
-  L->tile_gids = take(4 * d1);
+  L->depth_hist = take(4 * 1024);
   L->tile_ranges = take(8 * (size_t)tg.tiles_x * tg.tiles_y);
+  L->tile_gids = take(4 * d1);
+  L->zero_a_bytes = L->tile_gids - L->depth_hist;
   int rc = gsr_bin_workspace_bytes(n, width, height, max_dup, &L->bin_bytes);
   if (rc) return rc;
   L->bin = take(L->bin_bytes);
+  L->zero_b_bytes = bin_zero_bytes(n, max_dup);
   L->total = off;
   return GSR_OK;
 }
@@ -122,15 +128,15 @@ extern "C" int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t heig
   return GSR_OK;
 }
 
-extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
-                              size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
-                              uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
-                              gsr_frame_info *info_dev, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  GSR_REQUIRE(g && cam && workspace && image, "null pointer");
+// One frame on `stream`: 2 memsets + 10 kernels, no host synchronisation.  Exactly one of g / prepared is given.
+static int render_frame(const gsr_gaussians *g, const void *prepared, int64_t n, const gsr_camera *cam, int64_t max_dup,
+                        void *workspace, size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                        uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                        gsr_frame_info *info_dev, cudaStream_t stream) {
+  GSR_REQUIRE((g || prepared) && cam && workspace && image, "null pointer");
   GSR_REQUIRE(max_dup > 0, "max_dup must be positive");
   FrameLayout L;
-  int rc = frame_layout(g->n, cam->width, cam->height, max_dup, &L);
+  int rc = frame_layout(n, cam->width, cam->height, max_dup, &L);
   if (rc) return rc;
   if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("render workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
@@ -145,18 +151,71 @@ extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int
   float *rec = (float *)(ws + L.rec);
   uint32_t *order = (uint32_t *)(ws + L.order), *blend_rank = (uint32_t *)(ws + L.blend_rank);
   uint32_t *tile_gids = (uint32_t *)(ws + L.tile_gids), *tile_ranges = (uint32_t *)(ws + L.tile_ranges);
-  const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
-  if (info_dev) GSR_CHECK_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(gsr_frame_info), stream));
   uint32_t *depth_hist = (uint32_t *)(ws + L.depth_hist);
-  rc = gsr_preprocess_fwd(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span, rec, nullptr, nullptr,
-                          nullptr, nullptr, depth_hist, stream);
-  if (rc) return rc;
-  rc = gsr_bin(g->n, depth_key, depth_hist, tiles_touched, tile_span, cam->width, cam->height, max_dup, order,
-               windowed ? blend_rank : nullptr, tile_gids, tile_ranges, info_dev, ws + L.bin, L.bin_bytes, stream);
+  const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
+  // info_dev is NOT cleared here: status / n_dup_peak are sticky across frames (include/gsr_b200.h)
+  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.depth_hist, 0, L.zero_a_bytes, stream));  // depth_hist | tile_ranges
+  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.bin, 0, L.zero_b_bytes, stream));         // counters, look-back state, histograms
+  if (n > 0) {
+    if (prepared) {
+      GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
+      GSR_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 65535 * GSR_TILE && cam->height <= 65535 * GSR_TILE,
+                  "image size out of range");
+      GSR_REQUIRE(((uintptr_t)prepared & 255) == 0, "prepared model must be 256-byte aligned");
+      rc = launch_preprocess_prepared(prepared, n, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span,
+                                      rec, depth_hist, stream);
+    } else {
+      rc = preprocess_raw(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span, rec, nullptr, nullptr,
+                          nullptr, nullptr, depth_hist, stream, true);
+    }
+    if (rc) return rc;
+  }
+  rc = bin_impl(n, depth_key, depth_hist, tiles_touched, tile_span, cam->width, cam->height, max_dup, order,
+                windowed ? blend_rank : nullptr, tile_gids, tile_ranges, info_dev, ws + L.bin, L.bin_bytes, stream, true);
   if (rc) return rc;
   return gsr_blend_fwd(rec, tile_gids, tile_ranges, cam->width, cam->height, tile_row_begin, tile_row_end,
                        windowed ? blend_rank : nullptr, first_rank, last_rank, image, final_T, n_contrib, nullptr,
                        stream);
+}
+
+extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,
+                              size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                              uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                              gsr_frame_info *info_dev, void *stream) {
+  GSR_REQUIRE(g, "null gaussians");
+  return render_frame(g, nullptr, g->n, cam, max_dup, workspace, workspace_bytes, image, final_T, n_contrib, first_rank,
+                      last_rank, tile_row_begin, tile_row_end, info_dev, (cudaStream_t)stream);
+}
+
+extern "C" int gsr_render_prepared_fwd(const void *prepared, int64_t n, const gsr_camera *cam, int64_t max_dup,
+                                       void *workspace, size_t workspace_bytes, float *image, float *final_T,
+                                       uint32_t *n_contrib, uint32_t first_rank, uint32_t last_rank,
+                                       int32_t tile_row_begin, int32_t tile_row_end, gsr_frame_info *info_dev,
+                                       void *stream) {
+  GSR_REQUIRE(prepared && n >= 0 && n < (1ll << 31), "null prepared model / n out of range");
+  return render_frame(nullptr, prepared, n, cam, max_dup, workspace, workspace_bytes, image, final_T, n_contrib,
+                      first_rank, last_rank, tile_row_begin, tile_row_end, info_dev, (cudaStream_t)stream);
+}
+
+// A batch of views of one resident model: view v is enqueued on streams[v % n_lanes] with workspaces[v % n_lanes] and
+// info_dev[v % n_lanes] (frames of one lane are stream-ordered, lanes overlap: the latency-bound binning kernels of one
+// frame run under the issue-bound blend of another).  The caller owns streams and workspaces and joins the streams.
+extern "C" int gsr_render_views_fwd(const void *prepared, int64_t n, const gsr_camera *cams_host, int32_t n_views,
+                                    int64_t max_dup, void *const *workspaces, size_t workspace_bytes, int32_t n_lanes,
+                                    void *const *streams, float *images, int64_t image_stride_floats,
+                                    gsr_frame_info *info_dev) {
+  GSR_REQUIRE(prepared && cams_host && workspaces && streams && images, "null pointer");
+  GSR_REQUIRE(n_views >= 0 && n_lanes >= 1, "bad view / lane count");
+  for (int32_t v = 0; v < n_views; ++v) {
+    const int lane = v % n_lanes;
+    const gsr_camera *cam = cams_host + v;
+    GSR_REQUIRE(image_stride_floats >= (int64_t)3 * cam->width * cam->height, "image stride smaller than a frame");
+    int rc = render_frame(nullptr, prepared, n, cam, max_dup, workspaces[lane], workspace_bytes,
+                          images + (size_t)v * image_stride_floats, nullptr, nullptr, 0, 0xFFFFFFFFu, 0, -1,
+                          info_dev ? info_dev + lane : nullptr, (cudaStream_t)streams[lane]);
+    if (rc) return rc;
+  }
+  return GSR_OK;
 }
 
 // Gradients of one frame.  Must follow gsr_render_fwd of the SAME frame with the SAME workspace (the records and
@@ -186,22 +245,51 @@ extern "C" int gsr_render_bwd(const gsr_gaussians *g, const gsr_camera *cam, int
 }
 
 // Host-buffer frame: stands where the body of the reference's run_rasterization stands (rasterize.py:354-452).
+// Convenience entry (allocates and frees its device buffers on every call); a caller that renders more than one frame
+// keeps the model resident instead (gsr_prepare + gsr_render_prepared_fwd).
 extern "C" int gsr_render_host(const gsr_gaussians *gh, const gsr_camera *cam, int64_t max_dup, float *image_host,
                                gsr_frame_info *info_host) {
   GSR_REQUIRE(gh && cam && image_host, "null pointer");
-  GSR_REQUIRE(gh->n >= 0 && max_dup > 0, "bad sizes");
+  GSR_REQUIRE(gh->n >= 0 && gh->n < (1ll << 31) && max_dup > 0, "bad sizes");
+  GSR_REQUIRE(cam->width > 0 && cam->height > 0, "bad image size");
   const int64_t n = gh->n;
-  const size_t n1 = (size_t)(n > 0 ? n : 1);
+  const size_t img_bytes = sizeof(float) * 3 * (size_t)cam->width * cam->height;
+  if (info_host) memset(info_host, 0, sizeof *info_host);
+  if (n == 0) {  // nothing to upload, nothing to blend: the reference's screen stays zero
+    memset(image_host, 0, img_bytes);
+    return GSR_OK;
+  }
+  GSR_REQUIRE(gh->xyz && gh->log_scales && gh->rots && gh->opacity_logit && gh->sh, "null attribute pointer");
+  // Every attribute is uploaded as the smallest host span that contains its strided view (strides are kept), so all
+  // spans are computed and validated BEFORE anything is allocated or copied.
+  struct Attr {
+    const float *src;
+    int64_t sn, s1, c1, s2, c2, span;
+  } attr[5] = {{gh->xyz, gh->xyz_sn, gh->xyz_sc, 3, 0, 1, 0},
+               {gh->log_scales, gh->scale_sn, gh->scale_sc, 3, 0, 1, 0},
+               {gh->rots, gh->rot_sn, gh->rot_sc, 4, 0, 1, 0},
+               {gh->opacity_logit, gh->opacity_sn, 0, 1, 0, 1, 0},
+               {gh->sh, gh->sh_sn, gh->sh_sk, 16, gh->sh_sc, 3, 0}};
+  const int64_t dense = n * 59;
+  int64_t total = 0;
+  for (Attr &a : attr) {
+    GSR_REQUIRE(a.sn >= 0 && a.s1 >= 0 && a.s2 >= 0, "negative strides are not supported by the host-buffer entry");
+    a.span = 1 + (n - 1) * a.sn + (a.c1 - 1) * a.s1 + (a.c2 - 1) * a.s2;
+    a.span = (a.span + 3) & ~(int64_t)3;  // keep every attribute 16-byte aligned on the device
+    total += a.span;
+  }
+  if (total > 2 * dense + 64) {  // column views of a wider table etc.: refuse rather than upload the whole table 5 times
+    set_error("strided host views span %lld floats for %lld parameters; pass contiguous or planar arrays",
+              (long long)total, (long long)dense);
+    return GSR_ERR_INVALID_ARGUMENT;
+  }
   size_t ws_bytes = 0;
   int rc = gsr_render_workspace_bytes(n, cam->width, cam->height, max_dup, &ws_bytes);
   if (rc) return rc;
-  const size_t img_bytes = sizeof(float) * 3 * (size_t)cam->width * cam->height;
-  // device staging: parameters are repacked on the host side only if strided; contiguous views are copied as is
   float *d_params = nullptr, *d_image = nullptr;
   void *d_ws = nullptr;
   gsr_frame_info *d_info = nullptr;
   cudaStream_t stream = nullptr;
-  const size_t param_floats = n1 * (3 + 3 + 4 + 1 + 48);
   auto cleanup = [&]() {
     if (d_params) cudaFree(d_params);
     if (d_image) cudaFree(d_image);
@@ -219,30 +307,19 @@ extern "C" int gsr_render_host(const gsr_gaussians *gh, const gsr_camera *cam, i
     }                                                                                           \
   } while (0)
   GSR_HOST_CHECK(cudaStreamCreate(&stream));
-  GSR_HOST_CHECK(cudaMalloc(&d_params, sizeof(float) * param_floats));
+  GSR_HOST_CHECK(cudaMalloc(&d_params, sizeof(float) * (size_t)total));
   GSR_HOST_CHECK(cudaMalloc(&d_image, img_bytes));
   GSR_HOST_CHECK(cudaMalloc(&d_ws, ws_bytes));
   GSR_HOST_CHECK(cudaMalloc(&d_info, sizeof(gsr_frame_info)));
+  GSR_HOST_CHECK(cudaMemsetAsync(d_info, 0, sizeof(gsr_frame_info), stream));
   gsr_gaussians gd = *gh;
+  const float **dst[5] = {&gd.xyz, &gd.log_scales, &gd.rots, &gd.opacity_logit, &gd.sh};
   float *cursor = d_params;
-  // each attribute is uploaded as the smallest host span that contains its strided view; strides are kept
-  auto upload = [&](const float *src, int64_t sn, int64_t s1, int64_t c1, int64_t s2, int64_t c2, const float **dst) -> cudaError_t {
-    int64_t span = 1 + (n1 - 1) * sn + (c1 - 1) * s1 + (c2 - 1) * s2;
-    cudaError_t e = cudaMemcpyAsync(cursor, src, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, stream);
-    *dst = cursor;
-    cursor += span;
-    return e;
-  };
-  // spans never exceed the dense element count for the layouts torch produces (contiguous or planar views)
-  GSR_HOST_CHECK(upload(gh->xyz, gh->xyz_sn, gh->xyz_sc, 3, 0, 1, &gd.xyz));
-  GSR_HOST_CHECK(upload(gh->log_scales, gh->scale_sn, gh->scale_sc, 3, 0, 1, &gd.log_scales));
-  GSR_HOST_CHECK(upload(gh->rots, gh->rot_sn, gh->rot_sc, 4, 0, 1, &gd.rots));
-  GSR_HOST_CHECK(upload(gh->opacity_logit, gh->opacity_sn, 0, 1, 0, 1, &gd.opacity_logit));
-  GSR_HOST_CHECK(upload(gh->sh, gh->sh_sn, gh->sh_sk, 16, gh->sh_sc, 3, &gd.sh));
-  if ((size_t)(cursor - d_params) > param_floats) {
-    set_error("strided host views overlap-expand beyond the dense size; pass contiguous or planar arrays");
-    cleanup();
-    return GSR_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < 5; ++k) {
+    const int64_t exact = 1 + (n - 1) * attr[k].sn + (attr[k].c1 - 1) * attr[k].s1 + (attr[k].c2 - 1) * attr[k].s2;
+    GSR_HOST_CHECK(cudaMemcpyAsync(cursor, attr[k].src, sizeof(float) * (size_t)exact, cudaMemcpyHostToDevice, stream));
+    *dst[k] = cursor;
+    cursor += attr[k].span;
   }
   rc = gsr_render_fwd(&gd, cam, max_dup, d_ws, ws_bytes, d_image, nullptr, nullptr, 0, 0xFFFFFFFFu, 0, -1, d_info, stream);
   if (rc) {

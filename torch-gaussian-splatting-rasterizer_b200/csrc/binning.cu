@@ -161,9 +161,11 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
         const unsigned long long dup = prefix + total;
         ctr->n_dup = (uint32_t)(dup < capacity ? dup : capacity);
         if (info) {
-          info->n_dup = dup < 0xFFFFFFFFull ? (uint32_t)dup : 0xFFFFFFFFu;
+          const uint32_t dup32 = dup < 0xFFFFFFFFull ? (uint32_t)dup : 0xFFFFFFFFu;
+          info->n_dup = dup32;
           info->n_visible = (uint32_t)n;
-          if (dup > capacity) info->status = GSR_ERR_DUP_OVERFLOW;
+          atomicMax(&info->n_dup_peak, dup32);                       // sticky: frames of other streams may share the word
+          if (dup > capacity) info->status = GSR_ERR_DUP_OVERFLOW;  // sticky: only the caller clears it
         }
       }
     }
@@ -337,8 +339,18 @@ extern "C" int gsr_bin_workspace_bytes(int64_t n, int32_t width, int32_t height,
 extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
                        const uint32_t *tile_span, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
                        uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
-                       void *workspace, size_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+                       void *workspace, size_t workspace_bytes, void *stream) {
+  return bin_impl(n, depth_key, depth_hist, tiles_touched, tile_span, width, height, max_dup, depth_order, blend_rank,
+                  tile_gids, tile_ranges, info_dev, workspace, workspace_bytes, (cudaStream_t)stream, false);
+}
+
+// the zero-initialised head of the bin workspace: counters, look-back status, tile histograms, both sort scratches
+size_t gsr::bin_zero_bytes(int64_t n, int64_t max_dup) { return bin_layout(n, max_dup).order; }
+
+int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
+                  const uint32_t *tile_span, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+                  uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev,
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream, bool zeroed) {
   GSR_REQUIRE(depth_key && tiles_touched && tile_span && tile_gids && tile_ranges && workspace, "null pointer");
   GSR_REQUIRE(((uintptr_t)tile_span & 15) == 0, "tile_span must be 16-byte aligned");
   GSR_REQUIRE(n >= 0 && n < (1ll << 30) && max_dup > 0 && max_dup < (1ll << 30), "n / max_dup out of range");
@@ -357,10 +369,16 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   BinCounters *ctr = (BinCounters *)(ws + L.counters);
   unsigned long long *scan_status = (unsigned long long *)(ws + L.scan_status);
   uint32_t *tile_hist = (uint32_t *)(ws + L.tile_hist);
-  // counters + look-back status words + tile digit histograms are contiguous: one memset
-  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.depth_sort - L.counters, stream));
-  GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
-  if (n == 0) return GSR_OK;
+  // counters + look-back status words + tile digit histograms + the scratch of both sorts are contiguous: one memset
+  // (the whole-frame driver clears them together with its own zero-initialised buffers)
+  if (!zeroed) {
+    GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.counters, 0, L.order - L.counters, stream));
+    GSR_CHECK_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream));
+  }
+  if (n == 0) {  // no scan runs: the per-frame counters are cleared here (status / n_dup_peak stay as they are)
+    if (info_dev) GSR_CHECK_CUDA(cudaMemsetAsync(&info_dev->n_visible, 0, 2 * sizeof(uint32_t), stream));
+    return GSR_OK;
+  }
   if (!depth_order) depth_order = (uint32_t *)(ws + L.order);
 
   // 1. depth order of the Gaussians the reference's loop blends (bit 31 of tiles_touched), ties by index.  The first
@@ -373,7 +391,7 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   uint32_t *vis_count = &ctr->n_vis;
   rc = launch_sort_pairs(depth_key, nullptr, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
                          (uint32_t *)(ws + L.dvals_tmp), n, vis_count, 0, 32, s1, stream, true, depth_hist, tiles_touched,
-                         vis_count);
+                         vis_count, true);
   if (rc) return rc;
 
   // 2. prefix scan of the pair counts in depth order + pair emission + digit histograms of the tile ids
@@ -389,7 +407,8 @@ extern "C" int gsr_bin(int64_t n, const uint32_t *depth_key, const uint32_t *dep
   if (rc) return rc;
   uint32_t *sorted_tiles = (uint32_t *)(ws + L.tkeys_c);
   rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),
-                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false, tile_hist);
+                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false, tile_hist, nullptr,
+                         nullptr, true);
   if (rc) return rc;
 
   // 4. tile ranges from the sorted ids

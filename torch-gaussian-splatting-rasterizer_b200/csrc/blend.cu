@@ -244,12 +244,11 @@ using namespace gsr;
 
 // pixels per thread of the blend kernel: 4 unless GSR_BLEND_PX=2|4|8 is set (tuning knob, read once)
 static int blend_pixels_per_thread() {
-  static int px = 0;
-  if (px == 0) {
+  static const int px = [] {  // function-local static: initialised once, thread-safe
     const char *e = getenv("GSR_BLEND_PX");
-    px = e ? atoi(e) : 4;
-    if (px != 2 && px != 4 && px != 8) px = 4;
-  }
+    const int v = e ? atoi(e) : 4;
+    return (v != 2 && v != 4 && v != 8) ? 4 : v;
+  }();
   return px;
 }
 

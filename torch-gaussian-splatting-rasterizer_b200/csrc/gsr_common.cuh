@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/gsr_b200.h"
 
 namespace gsr {
@@ -27,6 +29,37 @@ void set_error(const char *fmt, ...);
     }                                                       \
   } while (0)
 #define GSR_LAUNCH_CHECK() GSR_CHECK_CUDA(cudaGetLastError())
+
+// ---- per-device state ------------------------------------------------------------------------------------------
+// One process may drive several GPUs (and several host threads): nothing device-specific is cached process-wide.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+inline int sm_count() {  // SM count of the CURRENT device
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// Opt a kernel into > 48 KB of dynamic shared memory, once per DEVICE (the attribute lives in the device's context;
+// a process-wide flag would leave the second GPU of a process unconfigured).  Racing first calls are harmless: both
+// set the same value.
+template <auto Kernel>
+inline cudaError_t ensure_dynamic_smem(int bytes) {
+  static std::atomic<int> done[kMaxDevices];
+  const int dev = current_device();
+  if (done[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev].store(bytes, std::memory_order_release);
+  return e;
+}
 
 // ---- single-rounding float ops ---------------------------------------------------------------
 // Decisions downstream (depth order, ceil of the radius, floor of the tile rect, alpha > 1/255) are
@@ -75,9 +108,22 @@ struct SortScratch {   // carved from a caller workspace
 size_t sort_scratch_bytes(int64_t n);
 // zeroes and carves; returns GSR_OK or error
 int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *out);
+int preprocess_raw(const gsr_gaussians *g, const gsr_camera *cam, int32_t row_begin, int32_t row_end,
+                   uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span, float *rec, float *cov3d, float *cov2d,
+                   int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist, cudaStream_t stream, bool hist_zeroed);
+int launch_preprocess_prepared(const void *prepared, int64_t n, const gsr_camera *cam, int row_begin, int row_end,
+                               uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span, float *rec,
+                               uint32_t *depth_hist, cudaStream_t stream);
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
-                      const uint32_t *ready_hist, const uint32_t *live_flags = nullptr, uint32_t *n_live_out = nullptr);
+                      const uint32_t *ready_hist, const uint32_t *live_flags = nullptr, uint32_t *n_live_out = nullptr,
+                      bool scratch_zeroed = false);
+// gsr_bin with the option of a workspace whose zero-initialised head (bin_zero_bytes) the caller has already cleared
+int bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
+             const uint32_t *tile_span, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,
+             uint32_t *blend_rank, uint32_t *tile_gids, uint32_t *tile_ranges, gsr_frame_info *info_dev, void *workspace,
+             size_t workspace_bytes, cudaStream_t stream, bool zeroed);
+size_t bin_zero_bytes(int64_t n, int64_t max_dup);
 
 }  // namespace gsr

@@ -131,6 +131,12 @@ __device__ __forceinline__ void covariance2d(const float S[9], const float cam[3
   c[3] = fadd(P[1][1], 0.3f);
 }
 
+// same, from the upper triangle S6 = (S00 S01 S02 S11 S12 S22) the reference symmetrises from (:234-243)
+__device__ __forceinline__ void covariance2d_sym(const float S6[6], const float cam[3], const gsr_camera &k, float c[4]) {
+  const float S[9] = {S6[0], S6[1], S6[2], S6[1], S6[3], S6[4], S6[2], S6[4], S6[5]};
+  covariance2d(S, cam, k, c);
+}
+
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // compute_covering_bbox, rasterize.py:163-197: radius and the reference's tile rect (tile units, as i64 there)
@@ -208,8 +214,10 @@ struct CullGaussian {
 __device__ __forceinline__ CullGaussian make_cull(float mx, float my, float A, float C, float B, float thr) {
   CullGaussian g;
   g.mx = mx; g.my = my; g.A = A; g.C = C; g.B = B;
-  g.kv = -B / (2.0f * C);
-  g.ku = -B / (2.0f * A);
+  // approximate divisions (2 ulp): the apex is only a parameter at which the exact parabola is evaluated, and the
+  // keep test carries a 2^-16 relative margin
+  g.kv = __fdividef(-B, 2.0f * C);
+  g.ku = __fdividef(-B, 2.0f * A);
   g.limit = thr - 1e-4f * (1.0f + fabsf(thr));
   return g;
 }

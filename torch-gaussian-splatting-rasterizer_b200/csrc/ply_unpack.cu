@@ -63,12 +63,7 @@ extern "C" int gsr_ply_unpack(const float *vertices, int64_t n, int32_t stride_f
   }
   if (n == 0) return GSR_OK;
   const size_t smem = sizeof(float) * kUnpackWarps * 32 * (size_t)stride_floats;
-  static bool configured = false;
-  if (!configured) {
-    GSR_CHECK_CUDA(cudaFuncSetAttribute(ply_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float) * kUnpackWarps * 32 * 256)));
-    configured = true;
-  }
+  GSR_CHECK_CUDA(ensure_dynamic_smem<&ply_unpack_kernel>((int)(sizeof(float) * kUnpackWarps * 32 * 256)));
   const unsigned blocks = (unsigned)ceil_div64(n, kUnpackWarps * 32);
   ply_unpack_kernel<<<blocks, kUnpackWarps * 32, smem, (cudaStream_t)stream>>>(vertices, n, stride_floats, cols, xyz,
                                                                              log_scales, rots, opacity_logit, sh_planar);

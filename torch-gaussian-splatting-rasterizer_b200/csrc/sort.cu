@@ -289,12 +289,12 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 
 // smallest supported tile that keeps the sort within one wave of CTAs (or the largest one)
 static int pick_items(int64_t n, int sms) {
-  static int cap = 0;  // GSR_SORT_MAX_ITEMS=4..24 caps the tile (smaller tiles leave shared memory to other streams)
-  if (cap == 0) {
+  // GSR_SORT_MAX_ITEMS=4..24 caps the tile (smaller tiles leave shared memory to other streams); read once, thread-safe
+  static const int cap = [] {
     const char *e = getenv("GSR_SORT_MAX_ITEMS");
-    cap = e ? atoi(e) : 24;
-    if (cap < 4 || cap > 24) cap = 24;
-  }
+    const int c = e ? atoi(e) : 24;
+    return (c < 4 || c > 24) ? 24 : c;
+  }();
   const int options[] = {4, 8, 12, 16, 20, 24};
   int best = 4;
   for (int it : options) {
@@ -304,11 +304,15 @@ static int pick_items(int64_t n, int sms) {
   }
   return best;
 }
-constexpr int kMinSortTile = kBigThreads * 4;  // scratch is sized for the smallest tile
+// Look-back status words: one row of 256 per tile and pass, for the tile size the launcher will pick for this n on the
+// current device (both are known on the host), so the per-frame memset covers kilobytes, not megabytes.
+static int64_t sort_tiles(int64_t n) {
+  const int64_t n1 = n > 0 ? n : 1;
+  return ceil_div64(n1, (int64_t)kBigThreads * pick_items(n1, sm_count()));
+}
 
 size_t sort_scratch_bytes(int64_t n) {
-  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kMinSortTile);
-  return align_up(sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * tiles * kRadix), 256);
+  return align_up(sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * sort_tiles(n) * kRadix), 256);
 }
 
 int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *out) {
@@ -316,7 +320,7 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
     set_error("sort workspace too small or misaligned (%zu < %zu)", bytes, sort_scratch_bytes(n));
     return GSR_ERR_WORKSPACE_TOO_SMALL;
   }
-  const int64_t tiles = ceil_div64(n > 0 ? n : 1, kMinSortTile);
+  const int64_t tiles = sort_tiles(n);
   uint32_t *p = (uint32_t *)workspace;
   out->hist = p;
   out->tickets = p + kMaxPasses * kRadix;
@@ -328,7 +332,7 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
-                      const uint32_t *ready_hist, const uint32_t *live_flags, uint32_t *n_live_out) {
+                      const uint32_t *ready_hist, const uint32_t *live_flags, uint32_t *n_live_out, bool scratch_zeroed) {
   GSR_REQUIRE(n >= 0 && n < (1ll << 30), "sort size out of range (must be < 2^30)");
   GSR_REQUIRE((live_flags == nullptr) == (n_live_out == nullptr), "live_flags and n_live_out go together");
   GSR_REQUIRE(!live_flags || n_dev == n_live_out, "a filtering sort counts its own survivors: n_dev must be n_live_out");
@@ -339,16 +343,10 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
   const int passes = (bits + 7) / 8;
   const int last_bits = bits - 8 * (passes - 1);
   const uint32_t last_mask = (1u << last_bits) - 1u;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    GSR_CHECK_CUDA(cudaGetDevice(&dev));
-    GSR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int items = pick_items(n, sms);
+  const int items = pick_items(n, sm_count());
   const int64_t tiles = ceil_div64(n, (int64_t)kBigThreads * items);
   const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
-  GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
+  if (!scratch_zeroed) GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
   const uint32_t *hist = ready_hist ? ready_hist : s.hist;  // digit counts may come from the producer of the keys
   if (!ready_hist) {
     int64_t want = ceil_div64(n, 256 * 16);
@@ -369,12 +367,7 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     const bool filter = p == 0 && live_flags != nullptr;
 #define GSR_SWEEP_LAUNCH(IT, F)                                                                                   \
   do {                                                                                                            \
-    static bool configured = false;                                                                               \
-    if (!configured) {                                                                                            \
-      GSR_CHECK_CUDA(cudaFuncSetAttribute(onesweep_kernel<IT, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                          (int)(sizeof(uint32_t) * 2 * kBigThreads * IT)));                        \
-      configured = true;                                                                                          \
-    }                                                                                                             \
+    GSR_CHECK_CUDA((ensure_dynamic_smem<&onesweep_kernel<IT, F>>((int)(sizeof(uint32_t) * 2 * kBigThreads * IT))));  \
     onesweep_kernel<IT, F><<<(unsigned)tiles, kBigThreads, smem, stream>>>(                                        \
         kin, vin, kout, vout, n, n_dev, hist + p * kRadix, s.status + p * s.status_stride, s.tickets + p,          \
         begin_bit + 8 * p, mask, live_flags, n_live_out);                                                         \
@@ -418,5 +411,5 @@ extern "C" int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in
   int rc = sort_scratch_carve(workspace, workspace_bytes, n, &s);
   if (rc) return rc;
   return launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, n_dev, begin_bit,
-                           end_bit, s, (cudaStream_t)stream, false, nullptr, nullptr, nullptr);
+                           end_bit, s, (cudaStream_t)stream, false, nullptr, nullptr, nullptr, false);
 }

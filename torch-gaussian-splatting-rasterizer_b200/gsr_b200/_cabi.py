@@ -39,7 +39,7 @@ class Gaussians(ctypes.Structure):
 
 
 class FrameInfo(ctypes.Structure):
-    _fields_ = [("status", c_uint32), ("n_visible", c_uint32), ("n_dup", c_uint32), ("reserved", c_uint32),
+    _fields_ = [("status", c_uint32), ("n_visible", c_uint32), ("n_dup", c_uint32), ("n_dup_peak", c_uint32),
                 ("warp_evals", c_uint64), ("pixel_evals", c_uint64)]
 
 
@@ -51,6 +51,14 @@ PROTOTYPES = {
     "gsr_render_workspace_bytes": [c_int64, c_int32, c_int32, c_int64, POINTER(c_size_t)],
     "gsr_render_fwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, c_size_t, c_void_p, c_void_p,
                        c_void_p, c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p],
+    "gsr_prepared_bytes": [c_int64, POINTER(c_size_t)],
+    "gsr_prepare": [POINTER(Gaussians), c_void_p, c_size_t, c_void_p],
+    "gsr_preprocess_prepared_fwd": [c_void_p, c_int64, POINTER(CameraStruct), c_int32, c_int32, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p],
+    "gsr_render_prepared_fwd": [c_void_p, c_int64, POINTER(CameraStruct), c_int64, c_void_p, c_size_t, c_void_p,
+                                c_void_p, c_void_p, c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p],
+    "gsr_render_views_fwd": [c_void_p, c_int64, POINTER(CameraStruct), c_int32, c_int64, POINTER(c_void_p), c_size_t,
+                             c_int32, POINTER(c_void_p), c_void_p, c_int64, c_void_p],
     "gsr_render_host": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, POINTER(FrameInfo)],
     "gsr_preprocess_fwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -215,16 +215,46 @@ def render_frame_banded(render_band: Callable[[Tuple[int, int], torch.Tensor], N
 # ----------------------------------------------------------------------------------------------
 # GPU front-ends
 # ----------------------------------------------------------------------------------------------
+def _agree_on_overflow(renderer) -> int:
+    """Sticky device status of this rank's frames, agreed across the ranks: 0 when every frame of every rank fit its
+    pair capacity, else the capacity (max over ranks of the worst frame's need, +10 %) everybody must redraw with."""
+    info = renderer.frame_info()
+    need = info["n_dup_peak"] if info["status"] != 0 else 0
+    if info["status"] not in (0, 4):
+        renderer.clear_status()
+        raise RuntimeError(f"libgsr_b200 frame status {info['status']}")
+    if _world()[1] > 1:
+        t = torch.tensor([need], dtype=torch.int64, device=renderer.device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        need = int(t.item())
+    if need:
+        renderer.clear_status()
+        return int(need * 1.1) + 1024
+    return 0
+
+
 def render_orbit(model, intr, views, degree: int = 3, renderer=None) -> torch.Tensor:
-    """[V,H,W,3]: config 4 - all views of an orbit, sharded by view across the initialised process group."""
+    """[V,H,W,3]: config 4 - all views of an orbit, sharded by view across the initialised process group.
+
+    Frames are enqueued without per-frame status reads; the device-side status is sticky, so ONE read after the orbit
+    (agreed across ranks with a MAX all-reduce of a single word) tells whether any frame of any rank overflowed its pair
+    capacity - in that case every rank raises its capacity to the reported need and the orbit is redrawn once."""
     from .camera import camera_for
     from .render import default_renderer
 
     r = renderer or default_renderer()
     cams = [camera_for(intr, v, degree) for v in views]
     side = torch.cuda.Stream() if _world()[1] > 1 else None
-    return render_views_sharded(lambda i, out: r.render(model, cams[i], out=out, check=False), len(views),
-                                (intr.height, intr.width, 3), r.device, side_stream=side)
+    for attempt in range(2):
+        out = render_views_sharded(lambda i, o: r.render(model, cams[i], out=o, check=False), len(views),
+                                   (intr.height, intr.width, 3), r.device, side_stream=side)
+        cap = _agree_on_overflow(r)
+        if not cap:
+            return out
+        if attempt == 1:
+            raise RuntimeError(f"orbit frames still overflow a pair capacity of {r.max_dup}")
+        r.reserve(model.n, intr.width, intr.height, max_dup=cap)
+    return out
 
 
 def tile_row_loads(model, cam, renderer=None) -> List[float]:
@@ -247,5 +277,13 @@ def render_banded(model, cam, renderer=None, row_loads: Optional[Sequence[float]
     r = renderer or default_renderer()
     if row_loads is None:
         row_loads = tile_row_loads(model, cam, r)
-    return render_frame_banded(lambda band, frame: r.render(model, cam, out=frame, tile_rows=band, check=False),
-                               row_loads, cam.width, cam.height, r.device)
+    for attempt in range(2):
+        out = render_frame_banded(lambda band, frame: r.render(model, cam, out=frame, tile_rows=band, check=False),
+                                  row_loads, cam.width, cam.height, r.device)
+        cap = _agree_on_overflow(r)  # sticky status, agreed across ranks (every rank must take the same branch)
+        if not cap:
+            return out
+        if attempt == 1:
+            raise RuntimeError(f"band still overflows a pair capacity of {r.max_dup}")
+        r.reserve(model.n, cam.width, cam.height, max_dup=cap)
+    return out

@@ -36,10 +36,29 @@ class GaussianModel:
     rots: torch.Tensor
     opacity: torch.Tensor
     sh: torch.Tensor  # logical [N,16,3], any strides
+    _prepared: Optional[torch.Tensor] = None  # view-independent half, blocked layout (include/gsr_b200.h: gsr_prepare)
 
     @property
     def n(self) -> int:
         return int(self.xyz.shape[0])
+
+    def prepare(self, force: bool = False) -> torch.Tensor:
+        """Compute (once) the prepared model a resident scene is rendered from: Sigma, sigmoid(opacity) and the record's
+        logarithms plus xyz / SH in 16-byte blocked rows.  Call ``prepare(force=True)`` after changing a parameter
+        tensor in place; the differentiable path never uses it (parameters change every step there)."""
+        if self._prepared is None or force:
+            _cabi.require_cuda()
+            need = ctypes.c_size_t()
+            _cabi.call("gsr_prepared_bytes", self.n, ctypes.byref(need))
+            buf = self._prepared
+            if buf is None or buf.numel() < need.value + 256:
+                buf = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
+            g = self.c_struct()
+            al = _align256(buf)
+            with torch.cuda.device(self.device):
+                _cabi.call("gsr_prepare", ctypes.byref(g), _cabi.ptr(al), al.numel(), _cabi.stream_handle())
+            self._prepared = buf
+        return _align256(self._prepared)
 
     @property
     def device(self):
@@ -114,23 +133,36 @@ def _align256(t: torch.Tensor) -> torch.Tensor:
 
 
 class Renderer:
-    """Owns the workspace for frames of one size class and enqueues whole frames on the current stream."""
+    """Owns the workspace for frames of one size class and enqueues whole frames on the current stream.
 
-    def __init__(self, device="cuda", dup_factor: float = 8.0):
+    Pair capacity (``max_dup``, the room for (Gaussian, tile) pairs): starts at ``dup_factor * n``; a frame that
+    overflows is detected on the device (sticky ``status`` in ``info_dev``) and redrawn once with the capacity it
+    reported; after a checked frame the capacity is tightened to 1.5x what that frame needed and then STAYS there for
+    frames of the same (n, W, H) - grids, memsets and look-back tables of the pair sort are sized by capacity.
+    """
+
+    def __init__(self, device="cuda", dup_factor: float = 8.0, use_prepared: bool = True):
         _cabi.require_cuda()
         self.device = torch.device(device)
         self.dup_factor = dup_factor
+        self.use_prepared = use_prepared
         self._ws: Optional[torch.Tensor] = None
         self._ws_key = None
+        self._cap_key = None    # (n, W, H) the current capacity was established for
         self.max_dup = 0
-        self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)  # gsr_frame_info (32 bytes)
+        self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)  # gsr_frame_info (32 bytes), sticky status
         self.adaptive_capacity = True
-        self.frame_serial = 0  # bumped by every frame: backward must replay the workspace of ITS forward
+        self.frame_serial = 0   # bumped by every frame: backward must replay the workspace of ITS forward
+        self._fwd_max_dup = 0   # capacity the last forward was enqueued with (what its backward must pass)
 
     # -- workspace ---------------------------------------------------------------------------
     def reserve(self, n: int, width: int, height: int, max_dup: Optional[int] = None) -> None:
-        max_dup = int(max_dup if max_dup is not None else max(self.max_dup, self.dup_factor * n, 1 << 16))
-        max_dup = min(max_dup, (1 << 30) - 1)
+        if max_dup is None:
+            if self._cap_key == (n, width, height) and self.max_dup > 0:
+                max_dup = self.max_dup          # established (possibly tightened) capacity is authoritative
+            else:
+                max_dup = max(int(self.dup_factor * n), 1 << 16)
+        max_dup = min(int(max_dup), (1 << 30) - 1)
         key = (n, width, height, max_dup)
         if self._ws is not None and self._ws_key == key:
             return
@@ -139,50 +171,81 @@ class Renderer:
         if self._ws is None or self._ws.numel() < need.value + 256:
             self._ws = None
             self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
-        self._ws_key, self.max_dup = key, max_dup
+        self._ws_key, self._cap_key, self.max_dup = key, (n, width, height), max_dup
+
+    def _enqueue(self, model: GaussianModel, cam: CameraStruct, out, final_T, n_contrib, first_rank, last_rank, rb, re,
+                 prepared: bool) -> None:
+        self.frame_serial += 1
+        self._fwd_max_dup = self.max_dup
+        ws = _align256(self._ws)
+        if prepared:
+            _cabi.call("gsr_render_prepared_fwd", _cabi.ptr(model.prepare()), model.n, ctypes.byref(cam), self.max_dup,
+                       _cabi.ptr(ws), ws.numel(), _cabi.ptr(out), _cabi.ptr(final_T), _cabi.ptr(n_contrib), first_rank,
+                       last_rank, rb, re, _cabi.ptr(self.info_dev), _cabi.stream_handle())
+        else:
+            g = model.c_struct()
+            _cabi.call("gsr_render_fwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws),
+                       ws.numel(), _cabi.ptr(out), _cabi.ptr(final_T), _cabi.ptr(n_contrib), first_rank, last_rank,
+                       rb, re, _cabi.ptr(self.info_dev), _cabi.stream_handle())
 
     # -- one frame ---------------------------------------------------------------------------
     def render(self, model: GaussianModel, cam: CameraStruct, out: Optional[torch.Tensor] = None,
                final_T: Optional[torch.Tensor] = None, n_contrib: Optional[torch.Tensor] = None,
                first_rank: int = 0, last_rank: int = U32_MAX, tile_rows: Optional[Sequence[int]] = None,
-               check: bool = True) -> torch.Tensor:
-        """Enqueue one frame; returns image ``[H,W,3]`` float32 (the reference's ``screen.transpose(1,0)``)."""
+               check: bool = True, prepared: Optional[bool] = None) -> torch.Tensor:
+        """Enqueue one frame; returns image ``[H,W,3]`` float32 (the reference's ``screen.transpose(1,0)``).
+
+        ``prepared`` (default: the renderer's ``use_prepared``) renders from ``model.prepare()``; ``False`` runs the
+        fused raw-parameter kernel (one-shot frames, the differentiable path).  The two are bit-identical.
+        ``check=False`` does not read the status back: it is sticky on the device, call ``check_status()`` after the
+        last frame of a sequence."""
         W, H = cam.width, cam.height
         self.reserve(model.n, W, H)
         if out is None:
             out = torch.empty((H, W, 3), dtype=torch.float32, device=self.device)
         assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (H, W, 3)
         rb, re = (0, -1) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+        prepared = self.use_prepared if prepared is None else prepared
         while True:
-            self.frame_serial += 1
-            ws = _align256(self._ws)
-            g = model.c_struct()
-            _cabi.call("gsr_render_fwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws),
-                       ws.numel(), _cabi.ptr(out), _cabi.ptr(final_T), _cabi.ptr(n_contrib), first_rank, last_rank,
-                       rb, re, _cabi.ptr(self.info_dev), _cabi.stream_handle())
+            self._enqueue(model, cam, out, final_T, n_contrib, first_rank, last_rank, rb, re, prepared)
             if not check:
                 return out
             info = self.frame_info()
-            if info["status"] == _cabi.GSR_ERR_DUP_OVERFLOW:  # grow once to the exact need and redo the frame
-                self.reserve(model.n, W, H, max_dup=int(info["n_dup"] * 1.1) + 1024)
+            if info["status"] == _cabi.GSR_ERR_DUP_OVERFLOW:  # grow once to the reported need and redo the frame
+                self.clear_status()
+                self.reserve(model.n, W, H, max_dup=int(max(info["n_dup"], info["n_dup_peak"]) * 1.1) + 1024)
                 continue
             if info["status"] != _cabi.GSR_OK:
+                self.clear_status()
                 raise _cabi.GsrError(info["status"], "frame failed")
-            # Tighten the pair capacity to what frames of this scene need (+30 %): grids and look-back tables of the
-            # pair sort are sized by capacity, so a loose one costs idle CTAs and memset bytes.  The allocation
-            # stays; an overflow on a later view is detected on the device and triggers one redraw.
-            tight = max(int(1.3 * info["n_dup"]) + 4096, 1 << 16)
-            if self.adaptive_capacity and tight < self.max_dup:
+            # Tighten the pair capacity to what frames of this scene need (+50 %); the allocation stays, and the
+            # tightened value is what reserve() keeps using.  An overflow on a later view is detected on the device.
+            tight = max(int(1.5 * info["n_dup"]) + 4096, 1 << 16)
+            if self.adaptive_capacity and tight < self.max_dup and tile_rows is None:
                 self.max_dup = tight
                 self._ws_key = (model.n, W, H, tight)
             return out
 
     def frame_info(self) -> Dict[str, int]:
-        """Synchronising read-back of the last frame's counters."""
+        """Synchronising read-back of the counters: n_visible / n_dup of the last frame, sticky status / n_dup_peak."""
         raw = self.info_dev.cpu().numpy().view(np.uint32)
-        return dict(status=int(raw[0]), n_visible=int(raw[1]), n_dup=int(raw[2]),
+        return dict(status=int(raw[0]), n_visible=int(raw[1]), n_dup=int(raw[2]), n_dup_peak=int(raw[3]),
                     warp_evals=int(raw[4]) | (int(raw[5]) << 32), pixel_evals=int(raw[6]) | (int(raw[7]) << 32))
 
+    def clear_status(self) -> None:
+        self.info_dev.zero_()
+
+    def check_status(self) -> Dict[str, int]:
+        """After a sequence of ``check=False`` frames: raise if ANY of them overflowed the pair capacity (their images
+        are invalid); the capacity is raised to what the worst frame needed, so the caller can simply redraw."""
+        info = self.frame_info()
+        if info["status"] != _cabi.GSR_OK:
+            self.clear_status()
+            if info["status"] == _cabi.GSR_ERR_DUP_OVERFLOW and self._cap_key is not None:
+                self.reserve(*self._cap_key, max_dup=int(info["n_dup_peak"] * 1.1) + 1024)
+            raise _cabi.GsrError(info["status"], f"a frame needed {info['n_dup_peak']} (Gaussian, tile) pairs, more than "
+                                                 f"the capacity it was drawn with; capacity raised to {self.max_dup}: redraw")
+        return info
 
     def backward(self, model: GaussianModel, cam: CameraStruct, final_T: torch.Tensor, n_contrib: torch.Tensor,
                  grad_image: torch.Tensor, tile_rows: Optional[Sequence[int]] = None):
@@ -198,7 +261,8 @@ class Renderer:
         rb, re = (0, -1) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
         ws = _align256(self._ws)
         g = model.c_struct()
-        _cabi.call("gsr_render_bwd", ctypes.byref(g), ctypes.byref(cam), self.max_dup, _cabi.ptr(ws), ws.numel(),
+        # the capacity the FORWARD was enqueued with (render() may have tightened self.max_dup since)
+        _cabi.call("gsr_render_bwd", ctypes.byref(g), ctypes.byref(cam), self._fwd_max_dup, _cabi.ptr(ws), ws.numel(),
                    _cabi.ptr(final_T), _cabi.ptr(n_contrib), _cabi.ptr(grad_image), _cabi.ptr(scratch), _cabi.ptr(d_xyz),
                    _cabi.ptr(d_ls), _cabi.ptr(d_rot), _cabi.ptr(d_op), _cabi.ptr(d_sh), *d_sh.stride(), rb, re,
                    _cabi.stream_handle())
@@ -215,7 +279,8 @@ class _RenderFunction(torch.autograd.Function):
         final_T = torch.empty((H, W), dtype=torch.float32, device=renderer.device)
         n_contrib = torch.zeros((H, W), dtype=torch.int32, device=renderer.device)
         out = torch.zeros((H, W, 3), dtype=torch.float32, device=renderer.device)
-        image = renderer.render(model, cam, out=out, final_T=final_T, n_contrib=n_contrib, tile_rows=tile_rows)
+        image = renderer.render(model, cam, out=out, final_T=final_T, n_contrib=n_contrib, tile_rows=tile_rows,
+                                prepared=False)  # parameters change every step: nothing view-independent to keep
         ctx.model, ctx.renderer, ctx.cam, ctx.tile_rows = model, renderer, cam, tile_rows
         ctx.serial = renderer.frame_serial
         ctx.save_for_backward(final_T, n_contrib)
@@ -265,7 +330,7 @@ def render(means, log_scales, quats, opacity_logits, sh, qvec, tvec, fx, fy, cam
     r = renderer or default_renderer()
     model = GaussianModel.from_tensors(means, log_scales, quats, opacity_logits, sh, device=r.device)
     cam = make_camera(qvec, tvec, fx, fy, cam_width, cam_height, width, height, degree)
-    return r.render(model, cam)
+    return r.render(model, cam, prepared=False)  # one frame of this model: the fused raw kernel, no prepared copy
 
 
 _lane_pool: Dict[int, list] = {}
@@ -282,11 +347,12 @@ def frame_lanes(count: int = 2, renderer: Optional[Renderer] = None):
 
 
 def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: Optional[Renderer] = None,
-                 out: Optional[torch.Tensor] = None, lanes: int = 3) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, lanes: int = 3, _retry: bool = False) -> torch.Tensor:
     """Render a list of ``scenes.View`` with one resident model: ``[V,H,W,3]`` (video / orbit path).
 
     Frames are independent, so they are spread round-robin over `lanes` renderers/streams; the call returns with
-    the current stream waiting on all of them."""
+    the current stream waiting on all of them.  A frame that overflows the pair capacity of its lane is detected (sticky
+    device status, one read per lane) and the whole batch is redrawn once with the capacity the worst frame reported."""
     from .camera import camera_for
 
     pool = frame_lanes(max(1, lanes), renderer)
@@ -308,18 +374,100 @@ def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: O
     for rend, strm in pool:
         if strm is not None:
             main.wait_stream(strm)
-    for rend, _ in pool[: min(len(pool), len(views))]:  # one synchronising status check per lane
-        info = rend.frame_info()
-        if info["status"] != _cabi.GSR_OK:
-            raise _cabi.GsrError(info["status"], f"a frame overflowed max_dup (needs {info['n_dup']} pairs); "
-                                                 f"call Renderer.reserve(..., max_dup=...) with a larger capacity")
+    # one synchronising status check per lane: the device-side status is sticky, so it covers EVERY frame of the lane
+    overflow = None
+    for rend, _ in pool[: min(len(pool), len(views))]:
+        try:
+            rend.check_status()
+        except _cabi.GsrError as exc:
+            if exc.status != _cabi.GSR_ERR_DUP_OVERFLOW:
+                raise
+            overflow = exc
+    if overflow is not None:
+        if _retry:
+            raise overflow
+        cap = max(rend.max_dup for rend, _ in pool)  # check_status() raised the capacity of the lanes that overflowed
+        for rend, _ in pool:
+            rend.reserve(model.n, intr.width, intr.height, max_dup=cap)
+        return render_views(model, intr, views, degree, renderer, out, lanes, _retry=True)
     return out
+
+
+class BatchRenderer:
+    """A batch of views of one resident (prepared) model through ONE C-ABI call, ``gsr_render_views_fwd``: the library
+    round-robins the frames over `lanes` caller-owned streams / workspaces, so consecutive frames overlap on the GPU
+    and the host pays one foreign call for the whole batch instead of one per frame."""
+
+    def __init__(self, lanes: int = 3, device="cuda", dup_factor: float = 8.0):
+        _cabi.require_cuda()
+        self.device = torch.device(device)
+        self.lanes = max(1, int(lanes))
+        self.dup_factor = dup_factor
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)]
+        self.info_dev = torch.zeros((self.lanes, 8), dtype=torch.int32, device=self.device)
+        self._ws: list = []
+        self._key = None
+        self.max_dup = 0
+        self.ws_bytes = 0
+
+    def reserve(self, n: int, width: int, height: int, max_dup: Optional[int] = None) -> None:
+        if max_dup is None:
+            max_dup = self.max_dup if (self._key is not None and self._key[:3] == (n, width, height)) else \
+                max(int(self.dup_factor * n), 1 << 16)
+        max_dup = min(int(max_dup), (1 << 30) - 1)
+        key = (n, width, height, max_dup)
+        if key == self._key:
+            return
+        need = ctypes.c_size_t()
+        _cabi.call("gsr_render_workspace_bytes", n, width, height, max_dup, ctypes.byref(need))
+        if not self._ws or self._ws[0].numel() < need.value + 256:
+            self._ws = []
+            self._ws = [torch.empty(need.value + 256, dtype=torch.uint8, device=self.device) for _ in range(self.lanes)]
+        self._key, self.max_dup, self.ws_bytes = key, max_dup, need.value
+
+    def render(self, model: GaussianModel, cams: Sequence[CameraStruct], out: Optional[torch.Tensor] = None,
+               check: bool = True) -> torch.Tensor:
+        """``[V,H,W,3]``; returns with the current stream waiting on every lane.  ``check`` reads the sticky status of
+        each lane once after the batch and redraws the batch with a larger capacity if any frame overflowed."""
+        V = len(cams)
+        W, H = cams[0].width, cams[0].height
+        assert all(c.width == W and c.height == H for c in cams)
+        self.reserve(model.n, W, H)
+        if out is None:
+            out = torch.empty((V, H, W, 3), dtype=torch.float32, device=self.device)
+        assert out.is_contiguous() and tuple(out.shape) == (V, H, W, 3) and out.dtype == torch.float32
+        prepared = model.prepare()
+        cam_arr = (CameraStruct * V)(*cams)
+        for attempt in range(2):
+            ws_arr = (ctypes.c_void_p * self.lanes)(*[_align256(w).data_ptr() for w in self._ws])
+            st_arr = (ctypes.c_void_p * self.lanes)(*[s.cuda_stream for s in self.streams])
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event(); ev.record(main)
+            for s_ in self.streams:
+                s_.wait_event(ev)
+            _cabi.call("gsr_render_views_fwd", _cabi.ptr(prepared), model.n, cam_arr, V, self.max_dup, ws_arr,
+                       self.ws_bytes, self.lanes, st_arr, _cabi.ptr(out), 3 * W * H, _cabi.ptr(self.info_dev))
+            for s_ in self.streams:
+                main.wait_stream(s_)
+            if not check:
+                return out
+            raw = self.info_dev.cpu().numpy().view(np.uint32)
+            if not raw[:, 0].any():
+                return out
+            self.info_dev.zero_()
+            if attempt == 1 or not (raw[:, 0] == _cabi.GSR_ERR_DUP_OVERFLOW).any():
+                raise _cabi.GsrError(int(raw[:, 0].max()), f"a frame of the batch failed (needs {int(raw[:, 3].max())} pairs)")
+            self.reserve(model.n, W, H, max_dup=int(int(raw[:, 3].max()) * 1.1) + 1024)
+        return out
 
 
 # ----------------------------------------------------------------------------------------------
 # stage-level wrappers (tests and profiling drive the stages one by one)
 # ----------------------------------------------------------------------------------------------
-def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, tile_rows=None) -> Dict[str, torch.Tensor]:
+def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, tile_rows=None,
+               prepared: bool = False) -> Dict[str, torch.Tensor]:
+    """Per-view preprocess stage.  ``prepared=True`` runs the kernel of the resident-scene path over ``model.prepare()``
+    (no debug outputs); its outputs are bit-identical to the raw kernel's."""
     _cabi.require_cuda()
     n, dev = model.n, model.device
     rb, re = (0, 1 << 30) if tile_rows is None else tile_rows
@@ -333,11 +481,17 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
                    cov2d=torch.empty((n, 2, 2), dtype=torch.float32, device=dev),
                    tile_rect=torch.empty((n, 4), dtype=torch.int32, device=dev),
                    mean2d=torch.empty((n, 2), dtype=torch.float32, device=dev))
-    g = model.c_struct()
-    _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), rb, re, _cabi.ptr(out["depth_key"]),
-               _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["tile_span"]), _cabi.ptr(out["rec"]),
-               _cabi.ptr(out.get("cov3d")), _cabi.ptr(out.get("cov2d")), _cabi.ptr(out.get("tile_rect")),
-               _cabi.ptr(out.get("mean2d")), _cabi.ptr(out["depth_hist"]), _cabi.stream_handle())
+    if prepared:
+        assert not debug, "debug outputs come from the raw kernel"
+        _cabi.call("gsr_preprocess_prepared_fwd", _cabi.ptr(model.prepare()), n, ctypes.byref(cam), rb, re,
+                   _cabi.ptr(out["depth_key"]), _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["tile_span"]),
+                   _cabi.ptr(out["rec"]), _cabi.ptr(out["depth_hist"]), _cabi.stream_handle())
+    else:
+        g = model.c_struct()
+        _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), rb, re, _cabi.ptr(out["depth_key"]),
+                   _cabi.ptr(out["tiles_touched"]), _cabi.ptr(out["tile_span"]), _cabi.ptr(out["rec"]),
+                   _cabi.ptr(out.get("cov3d")), _cabi.ptr(out.get("cov2d")), _cabi.ptr(out.get("tile_rect")),
+                   _cabi.ptr(out.get("mean2d")), _cabi.ptr(out["depth_hist"]), _cabi.stream_handle())
     # views of the span: the clipped (and culling-shrunk) tile rect as u16 x0,y0,x1,y1 and the 64-bit keep mask
     out["rect"] = out["tile_span"].view(torch.int16)[:, :4]
     out["tile_mask"] = out["tile_span"][:, 2:4]
