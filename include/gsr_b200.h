@@ -137,9 +137,33 @@ int gsr_render_views_fwd(const void *prepared, int64_t n, const gsr_camera *cams
                          float *images, int64_t image_stride_floats, gsr_frame_info *info_dev);
 
 /* Same frame with HOST buffers: uploads the parameters, renders, downloads the image, synchronises.
- * This is the call that stands where the reference's run_rasterization body stands (:354-452). */
+ * This is the call that stands where the reference's run_rasterization body stands (:354-452).  One-shot
+ * convenience: it allocates and frees its device buffers on every call. */
 int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t max_dup, float *image_host,
                     gsr_frame_info *info_host);
+
+/* Host-buffer frames as a pipeline (the reference keeps its Gaussians in host tensors and moves them with .to(device),
+ * :353-358; a caller in that position renders through this object).  All device memory, three streams and the events
+ * are created once.  A frame is PCIe-bound (59 floats per Gaussian up, one image down); the renderer hides the rest:
+ * the upload is cut into chunks of Gaussians and the per-Gaussian preprocess kernel runs on each chunk as soon as it
+ * has landed, binning + blend follow the last chunk, the image goes down on a third stream, and up to `depth` frames
+ * are in flight so the upload of frame k+1 overlaps the render and read-back of frame k.
+ *   g_host: dense host arrays xyz[n,3], log_scales[n,3], rots[n,4], opacity_logit[n] (unit strides) and SH either as
+ *   the planar [3,16,n] block (strides 1, n, 16n - what read_color_components builds, utils.py:21-31) or dense [n,16,3].
+ *   Pinned host memory gives asynchronous copies; pageable memory works but serialises.
+ * submit() enqueues one frame and returns a ticket; the host buffers (inputs and image) must stay valid and unchanged
+ * until wait(ticket) returns.  At most `depth` tickets are outstanding: submit() blocks on the oldest one otherwise.
+ * wait() returns GSR_ERR_DUP_OVERFLOW (image invalid) when the frame needed more than max_dup pairs; info_host (may be
+ * NULL) receives the frame's counters.  render() = submit + wait.  Not thread-safe per object. */
+typedef struct gsr_host_renderer gsr_host_renderer;
+int gsr_host_renderer_create(int64_t n_max, int32_t width, int32_t height, int64_t max_dup, int32_t depth,
+                             gsr_host_renderer **out);
+int gsr_host_renderer_destroy(gsr_host_renderer *h);
+int gsr_host_renderer_submit(gsr_host_renderer *h, const gsr_gaussians *g_host, const gsr_camera *cam,
+                             float *image_host, int32_t *ticket);
+int gsr_host_renderer_wait(gsr_host_renderer *h, int32_t ticket, gsr_frame_info *info_host);
+int gsr_host_renderer_render(gsr_host_renderer *h, const gsr_gaussians *g_host, const gsr_camera *cam,
+                             float *image_host, gsr_frame_info *info_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Stages (each usable on its own; the tests drive them one by one)

@@ -101,8 +101,9 @@ def test_gradients_of_a_scene_larger_than_the_default_capacity():
     leaves = [t.clone().requires_grad_(True) for t in (model.xyz, model.log_scales, model.rots, model.opacity)]
     sh = model.sh.contiguous().clone().requires_grad_(True)
     (R.render_differentiable(*leaves, sh, cam, renderer=fixed) * torch.from_numpy(G).cuda()).sum().backward()
-    for k, t in zip(KEYS, leaves + [sh]):
-        assert torch.equal(grads[k], t.grad), k
+    for k, t in zip(KEYS, leaves + [sh]):  # float atomics accumulate in a run-dependent order: equal to rounding noise
+        scale = max(float(t.grad.abs().max()), 1e-6)
+        assert float((grads[k] - t.grad).abs().max()) <= 1e-5 * scale, k
     tight = R.Renderer()
     tight.render(model, cam)
     assert tight.max_dup < max(int(tight.dup_factor * n), 1 << 16)  # the tightening really happened

@@ -351,7 +351,13 @@ def test_prepared_preprocess_is_bit_identical(name, R):
     assert torch.equal(img_p, img_r)
     sh_i = model.sh.contiguous()                       # [N,16,3] interleaved
     m2 = R.GaussianModel(model.xyz, model.log_scales, model.rots, model.opacity, sh_i)
-    assert m2.sh.stride() != model.sh.stride() and torch.equal(m2.prepare(), model.prepare())
+    import ctypes
+
+    from gsr_b200 import _cabi
+    need = ctypes.c_size_t()
+    _cabi.call("gsr_prepared_bytes", model.n, ctypes.byref(need))
+    assert m2.sh.stride() != model.sh.stride()
+    assert torch.equal(m2.prepare()[: need.value], model.prepare()[: need.value])
 
 
 def test_generate_video_cli_branch(tmp_path):
@@ -527,3 +533,39 @@ def test_host_buffer_entry_point(golden):
                ctypes.byref(info))
     assert info.status == 0 and info.n_visible == int(golden(name)["n_blended"])
     assert np.abs(img - golden(name)["image"]).max() < 2e-4
+
+
+def test_host_renderer_pipeline(golden, R):
+    """gsr_host_renderer: host tensors in, host image out, chunked upload overlapped with the per-chunk preprocess,
+    several frames in flight.  Same image as the resident path; planar and dense SH; overflow reported per ticket."""
+    cloud = scenes.synth_v1(50_011, 77, scale_factor=0.3)   # enough Gaussians for 8 chunks, ragged chunk borders
+    intr = scenes.Intrinsics.synthetic(320, 200)
+    views = scenes.orbit_views(4, total=16)
+    cams = [camera.camera_for(intr, v, 3) for v in views]
+    model = R.GaussianModel.from_cloud(cloud)
+    want = [R.Renderer().render(model, c).cpu() for c in cams]
+    host = [torch.from_numpy(a).pin_memory() for a in (cloud.xyz, cloud.scales, cloud.rots, cloud.opacity)]
+    sh_planar = torch.from_numpy(cloud.sh_planar()).pin_memory().permute(2, 1, 0)
+    hr = R.HostRenderer(cloud.n, intr.width, intr.height, depth=2)
+    outs = [torch.empty((intr.height, intr.width, 3)).pin_memory() for _ in cams]
+    tickets = []
+    for c, o in zip(cams, outs):           # more submissions than slots: the third blocks on the first
+        tickets.append(hr.submit(*host, sh_planar, c, o))
+    infos = [hr.wait(t) for t in tickets]
+    for o, w, info in zip(outs, want, infos):
+        assert torch.equal(o, w) and info["status"] == 0 and info["n_visible"] > 0
+    sh_dense = sh_planar.contiguous().pin_memory()
+    assert torch.equal(hr.render(*host, sh_dense, cams[1]), want[1])
+    # a smaller scene through the same object (n <= n_max), then one that does not fit the pair capacity
+    sub = cloud.subset(np.arange(1000))
+    sm = [torch.from_numpy(np.ascontiguousarray(a)) for a in (sub.xyz, sub.scales, sub.rots, sub.opacity)]
+    sh_sub = torch.from_numpy(sub.sh_planar()).permute(2, 1, 0)
+    got = hr.render(*sm, sh_sub, cams[0])
+    assert torch.equal(got, R.Renderer().render(R.GaussianModel.from_cloud(sub), cams[0]).cpu())
+    hr.close()
+    tiny = R.HostRenderer(cloud.n, intr.width, intr.height, max_dup=1000, depth=1)
+    from gsr_b200 import _cabi
+    with pytest.raises(_cabi.GsrError) as exc:
+        tiny.render(*host, sh_planar, cams[0])
+    assert exc.value.status == _cabi.GSR_ERR_DUP_OVERFLOW
+    tiny.close()

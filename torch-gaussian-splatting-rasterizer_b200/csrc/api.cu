@@ -128,54 +128,88 @@ extern "C" int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t heig
   return GSR_OK;
 }
 
-// One frame on `stream`: 2 memsets + 10 kernels, no host synchronisation.  Exactly one of g / prepared is given.
-static int render_frame(const gsr_gaussians *g, const void *prepared, int64_t n, const gsr_camera *cam, int64_t max_dup,
-                        void *workspace, size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
-                        uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
-                        gsr_frame_info *info_dev, cudaStream_t stream) {
-  GSR_REQUIRE((g || prepared) && cam && workspace && image, "null pointer");
+// ---- a frame in three steps (shared by the single-call entry points and by the host pipeline, host.cu) ----
+int gsr::frame_buffers(int64_t n, int width, int height, int64_t max_dup, void *workspace, size_t workspace_bytes,
+                       FrameBuffers *fb) {
+  GSR_REQUIRE(workspace && fb, "null pointer");
   GSR_REQUIRE(max_dup > 0, "max_dup must be positive");
   FrameLayout L;
-  int rc = frame_layout(n, cam->width, cam->height, max_dup, &L);
+  int rc = frame_layout(n, width, height, max_dup, &L);
   if (rc) return rc;
   if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("render workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
     return GSR_ERR_WORKSPACE_TOO_SMALL;
   }
+  char *ws = (char *)workspace;
+  fb->depth_key = (uint32_t *)(ws + L.depth_key);
+  fb->tiles_touched = (uint32_t *)(ws + L.tiles_touched);
+  fb->tile_span = (uint32_t *)(ws + L.tile_span);
+  fb->rec = (float *)(ws + L.rec);
+  fb->order = (uint32_t *)(ws + L.order);
+  fb->blend_rank = (uint32_t *)(ws + L.blend_rank);
+  fb->depth_hist = (uint32_t *)(ws + L.depth_hist);
+  fb->tile_ranges = (uint32_t *)(ws + L.tile_ranges);
+  fb->tile_gids = (uint32_t *)(ws + L.tile_gids);
+  fb->bin = ws + L.bin;
+  fb->bin_bytes = L.bin_bytes;
+  fb->zero_a = ws + L.depth_hist;
+  fb->zero_a_bytes = L.zero_a_bytes;
+  fb->zero_b_bytes = L.zero_b_bytes;
+  return GSR_OK;
+}
+
+// zero-initialised parts of the workspace: depth_hist | tile_ranges, and the head of the binning workspace
+int gsr::frame_begin(const FrameBuffers &fb, cudaStream_t stream) {
+  GSR_CHECK_CUDA(cudaMemsetAsync(fb.zero_a, 0, fb.zero_a_bytes, stream));
+  GSR_CHECK_CUDA(cudaMemsetAsync(fb.bin, 0, fb.zero_b_bytes, stream));
+  return GSR_OK;
+}
+
+// binning + blend of a frame whose per-Gaussian outputs (depth_key .. rec, depth_hist) are in place
+int gsr::frame_finish(const FrameBuffers &fb, int64_t n, const gsr_camera *cam, int64_t max_dup, float *image,
+                      gsr_frame_info *info_dev, cudaStream_t stream, float *final_T, uint32_t *n_contrib,
+                      uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end) {
+  const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
+  int rc = bin_impl(n, fb.depth_key, fb.depth_hist, fb.tiles_touched, fb.tile_span, cam->width, cam->height, max_dup,
+                    fb.order, windowed ? fb.blend_rank : nullptr, fb.tile_gids, fb.tile_ranges, info_dev, fb.bin,
+                    fb.bin_bytes, stream, true);
+  if (rc) return rc;
+  return gsr_blend_fwd(fb.rec, fb.tile_gids, fb.tile_ranges, cam->width, cam->height, tile_row_begin, tile_row_end,
+                       windowed ? fb.blend_rank : nullptr, first_rank, last_rank, image, final_T, n_contrib, nullptr,
+                       stream);
+}
+
+// One frame on `stream`: 2 memsets + 10 kernels, no host synchronisation.  Exactly one of g / prepared is given.
+// info_dev is NOT cleared here: status / n_dup_peak are sticky across frames (include/gsr_b200.h).
+static int render_frame(const gsr_gaussians *g, const void *prepared, int64_t n, const gsr_camera *cam, int64_t max_dup,
+                        void *workspace, size_t workspace_bytes, float *image, float *final_T, uint32_t *n_contrib,
+                        uint32_t first_rank, uint32_t last_rank, int32_t tile_row_begin, int32_t tile_row_end,
+                        gsr_frame_info *info_dev, cudaStream_t stream) {
+  GSR_REQUIRE((g || prepared) && cam && workspace && image, "null pointer");
+  FrameBuffers fb;
+  int rc = frame_buffers(n, cam->width, cam->height, max_dup, workspace, workspace_bytes, &fb);
+  if (rc) return rc;
   const TileGrid tg = make_grid(cam->width, cam->height);
   if (tile_row_begin < 0) tile_row_begin = 0;
   if (tile_row_end < 0 || tile_row_end > tg.tiles_y) tile_row_end = tg.tiles_y;
-  char *ws = (char *)workspace;
-  uint32_t *depth_key = (uint32_t *)(ws + L.depth_key), *tiles_touched = (uint32_t *)(ws + L.tiles_touched);
-  uint32_t *tile_span = (uint32_t *)(ws + L.tile_span);
-  float *rec = (float *)(ws + L.rec);
-  uint32_t *order = (uint32_t *)(ws + L.order), *blend_rank = (uint32_t *)(ws + L.blend_rank);
-  uint32_t *tile_gids = (uint32_t *)(ws + L.tile_gids), *tile_ranges = (uint32_t *)(ws + L.tile_ranges);
-  uint32_t *depth_hist = (uint32_t *)(ws + L.depth_hist);
-  const bool windowed = !(first_rank == 0 && last_rank == 0xFFFFFFFFu);
-  // info_dev is NOT cleared here: status / n_dup_peak are sticky across frames (include/gsr_b200.h)
-  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.depth_hist, 0, L.zero_a_bytes, stream));  // depth_hist | tile_ranges
-  GSR_CHECK_CUDA(cudaMemsetAsync(ws + L.bin, 0, L.zero_b_bytes, stream));         // counters, look-back state, histograms
+  rc = frame_begin(fb, stream);
+  if (rc) return rc;
   if (n > 0) {
     if (prepared) {
       GSR_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
       GSR_REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 65535 * GSR_TILE && cam->height <= 65535 * GSR_TILE,
                   "image size out of range");
       GSR_REQUIRE(((uintptr_t)prepared & 255) == 0, "prepared model must be 256-byte aligned");
-      rc = launch_preprocess_prepared(prepared, n, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span,
-                                      rec, depth_hist, stream);
+      rc = launch_preprocess_prepared(prepared, n, cam, tile_row_begin, tile_row_end, fb.depth_key, fb.tiles_touched,
+                                      fb.tile_span, fb.rec, fb.depth_hist, stream);
     } else {
-      rc = preprocess_raw(g, cam, tile_row_begin, tile_row_end, depth_key, tiles_touched, tile_span, rec, nullptr, nullptr,
-                          nullptr, nullptr, depth_hist, stream, true);
+      rc = preprocess_raw(g, cam, tile_row_begin, tile_row_end, fb.depth_key, fb.tiles_touched, fb.tile_span, fb.rec,
+                          nullptr, nullptr, nullptr, nullptr, fb.depth_hist, stream, true);
     }
     if (rc) return rc;
   }
-  rc = bin_impl(n, depth_key, depth_hist, tiles_touched, tile_span, cam->width, cam->height, max_dup, order,
-                windowed ? blend_rank : nullptr, tile_gids, tile_ranges, info_dev, ws + L.bin, L.bin_bytes, stream, true);
-  if (rc) return rc;
-  return gsr_blend_fwd(rec, tile_gids, tile_ranges, cam->width, cam->height, tile_row_begin, tile_row_end,
-                       windowed ? blend_rank : nullptr, first_rank, last_rank, image, final_T, n_contrib, nullptr,
-                       stream);
+  return frame_finish(fb, n, cam, max_dup, image, info_dev, stream, final_T, n_contrib, first_rank, last_rank,
+                      tile_row_begin, tile_row_end);
 }
 
 extern "C" int gsr_render_fwd(const gsr_gaussians *g, const gsr_camera *cam, int64_t max_dup, void *workspace,

@@ -74,7 +74,8 @@ __device__ __forceinline__ uint32_t span_pairs(const Span &s) {
 // Walks the compacted depth order: prefix scan of the pair counts (decoupled look-back across CTAs), emission of the
 // (tile id, Gaussian id) pairs in depth order, blend ranks, and the digit histograms of the tile ids.
 __global__ void __launch_bounds__(kScanThreads, 4)
-scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ order, const uint4 *__restrict__ span,
+scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ order_x0, uint32_t *__restrict__ order_x1,
+                 const uint32_t *__restrict__ depth_hist, const uint4 *__restrict__ span,
                  int tiles_x, unsigned long long capacity, unsigned long long *status, BinCounters *ctr,
                  uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids, uint32_t *__restrict__ blend_rank,
                  uint32_t *__restrict__ tile_hist /*[2][256]*/, gsr_frame_info *info) {
@@ -92,6 +93,10 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
   const int64_t n = (int64_t)*n_dev;  // entries of `order`: the Gaussians the reference's loop blends
   if ((int64_t)tile * kScanTile >= n && tile != 0) return;  // grid sized for the capacity; tile 0 always runs (totals for n == 0)
   const int64_t first = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
+  // The adaptive depth sort leaves the order in X0 or X1 depending on how many of its passes were identities (sort.cu);
+  // when it is X0 the ids are copied to X1 on the way, so that X1 (the caller's depth_order) always holds the order.
+  const bool from_x0 = n > 0 && sorted_buffer_index(depth_hist, 4, (uint32_t)n) == 0;
+  const uint32_t *order = from_x0 ? order_x0 : order_x1;
 
   uint32_t gid[kScanItems], cnt[kScanItems];
   uint4 sp[kScanItems];
@@ -103,6 +108,11 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j)
     if (gid[j] != 0xFFFFFFFFu) sp[j] = __ldg(span + gid[j]);  // the only gather: 16 bytes per Gaussian
+  if (from_x0) {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+      if (gid[j] != 0xFFFFFFFFu) order_x1[first + j] = gid[j];
+  }
   unsigned long long mine = 0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
@@ -391,14 +401,16 @@ int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hi
   uint32_t *vis_count = &ctr->n_vis;
   rc = launch_sort_pairs(depth_key, nullptr, (uint32_t *)(ws + L.dkeys_out), depth_order, (uint32_t *)(ws + L.dkeys_tmp),
                          (uint32_t *)(ws + L.dvals_tmp), n, vis_count, 0, 32, s1, stream, true, depth_hist, tiles_touched,
-                         vis_count, true);
+                         vis_count, true, true);
+  const uint32_t *depth_hist_used = depth_hist ? depth_hist : s1.hist;
   if (rc) return rc;
 
   // 2. prefix scan of the pair counts in depth order + pair emission + digit histograms of the tile ids
   uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
   const size_t stage_bytes = sizeof(uint32_t) * kStageWords * (kScanThreads / 32);
   scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, stage_bytes, stream>>>(
-      vis_count, depth_order, (const uint4 *)tile_span, tg.tiles_x, (unsigned long long)max_dup, scan_status, ctr, tkeys_a,
+      vis_count, (const uint32_t *)(ws + L.dvals_tmp), depth_order, depth_hist_used, (const uint4 *)tile_span, tg.tiles_x,
+      (unsigned long long)max_dup, scan_status, ctr, tkeys_a,
       tgids_a, blend_rank, tile_hist, info_dev);
   GSR_LAUNCH_CHECK();
 
@@ -408,7 +420,7 @@ int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hi
   uint32_t *sorted_tiles = (uint32_t *)(ws + L.tkeys_c);
   rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),
                          (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false, tile_hist, nullptr,
-                         nullptr, true);
+                         nullptr, true, false);
   if (rc) return rc;
 
   // 4. tile ranges from the sorted ids

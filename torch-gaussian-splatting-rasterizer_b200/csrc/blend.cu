@@ -29,7 +29,15 @@ namespace gsr {
 
 constexpr float kParkedY = 1e18f;
 
-template <int PX, bool COUNT, bool RANKED, bool TRACK>
+// BULK selects how a batch of records reaches shared memory:
+//   false  cp.async (LDGSTS): every thread gathers its records with three 16-byte asynchronous copies, completion by
+//          cp.async.wait_group + the batch barrier;
+//   true   cp.async.bulk (the TMA unit, SASS UBLKCP): one 48-byte bulk copy per record, completion counted in bytes
+//          by an mbarrier (expect_tx / complete_tx) that the consumers wait on - no wait_group.
+// Both deliver the same bytes to the same slots; the image is bit-identical (tests/test_gpu_edges.py).  Which one is
+// the default is a measurement (profiles/r02_notes.md): the lists are GATHERS of scattered 48-byte records, so the
+// bulk path needs one TMA operation per record, issued from uniform registers one lane at a time.
+template <int PX, bool COUNT, bool RANKED, bool TRACK, bool BULK>
 __global__ void __launch_bounds__(256 / PX)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
@@ -38,7 +46,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   constexpr int THREADS = 256 / PX;
   constexpr int kBatch = PX >= 8 ? 64 : 128;  // records per staged batch (smaller CTAs keep more CTAs resident)
   constexpr int PER = kBatch / THREADS;  // records gathered per thread and batch
-  __shared__ __align__(16) float s_rec[2][kBatch * GSR_REC_FLOATS];
+  __shared__ __align__(128) float s_rec[2][kBatch * GSR_REC_FLOATS];
+  __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
@@ -53,24 +62,38 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
   const float fx = (float)px;
 
+  // A terminated (or unwritable) pixel is parked at y = 1e18: it fails the power test like any other miss, and "all
+  // my pixels are parked" is read off fy itself - no live counter to maintain in the blend path.
   float fy[PX], T[PX], C0[PX], C1[PX], C2[PX];
   uint32_t last[PX];
-  int live = 0;
 #pragma unroll
   for (int k = 0; k < PX; ++k) {
     const bool writable = px < width - 1 && py0 + k * R < height - 1;  // Q8: last column / row are never written
     fy[k] = writable ? (float)(py0 + k * R) : kParkedY;
-    live += writable;
     T[k] = 1.0f;
     C0[k] = C1[k] = C2[k] = 0.0f;
     last[k] = 0;
   }
+  auto alive = [&]() {  // some pixel of this thread can still change
+    float m = fy[0];
+#pragma unroll
+    for (int k = 1; k < PX; ++k) m = fminf(m, fy[k]);
+    return m < 0.5f * kParkedY;
+  };
   unsigned long long my_iters = 0, my_evals = 0;
   // -0.0f, but only the host knows (kernel argument): ptxas folds fma(a, b, -0) back into a contractable multiply
   const f32x2 neg_zero2 = pack2(neg_zero, neg_zero);
 
   const uint32_t total = range.y - range.x;
   const int num_batches = (int)((total + kBatch - 1) / kBatch);
+  if (BULK) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
   uint32_t gnext[PER];
   auto load_ids = [&](int b) {
 #pragma unroll
@@ -79,23 +102,34 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       gnext[r] = (b < num_batches && idx < range.y) ? __ldg(gids + idx) : 0xFFFFFFFFu;
     }
   };
-  auto issue = [&](int buf) {
+  auto issue = [&](int buf, int b) {  // gather batch b (ids in gnext) into buffer buf
+    if (BULK) {
+      // bytes this batch will deliver: 48 per real record (slots past the end of the list get a sentinel store)
+      if (tid == 0 && b < num_batches) {
+        const uint32_t cnt = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
+        mbar_expect_tx_arrive(&s_bar[buf], cnt * (uint32_t)(GSR_REC_FLOATS * sizeof(float)));
+      }
+    }
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
       float *dst = &s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS];
       if (gnext[r] != 0xFFFFFFFFu) {
         const float4 *src = rec + (size_t)gnext[r] * 3;
-        cp_async16(dst, src);
-        cp_async16(dst + 4, src + 1);
-        cp_async16(dst + 8, src + 2);
+        if (BULK) {
+          bulk_copy_g2s(dst, src, GSR_REC_FLOATS * sizeof(float), &s_bar[buf]);
+        } else {
+          cp_async16(dst, src);
+          cp_async16(dst + 4, src + 1);
+          cp_async16(dst + 8, src + 2);
+        }
       } else {
         dst[5] = __int_as_float(0x7f800000);  // slot past the end of the list: thr = +inf, no pixel passes the test
       }
     }
-    cp_async_commit();
+    if (!BULK) cp_async_commit();
   };
   load_ids(0);
-  issue(0);
+  issue(0, 0);
   uint32_t gcur[PER];
 #pragma unroll
   for (int r = 0; r < PER; ++r) gcur[r] = gnext[r];
@@ -106,11 +140,15 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     uint32_t gmine[PER];
 #pragma unroll
     for (int r = 0; r < PER; ++r) gmine[r] = gcur[r];
-    issue(buf ^ 1);  // batch b+1 (empty group when past the end)
+    issue(buf ^ 1, b + 1);  // batch b+1 (nothing when past the end)
 #pragma unroll
     for (int r = 0; r < PER; ++r) gcur[r] = gnext[r];
     load_ids(b + 2);
-    cp_async_wait<1>();  // batch b has landed for this thread's copies
+    if (BULK) {
+      mbar_wait(&s_bar[buf], (unsigned)((b >> 1) & 1));  // every byte of batch b has landed (visible to all waiters)
+    } else {
+      cp_async_wait<1>();  // batch b has landed for this thread's copies
+    }
     if (RANKED) {        // progressive renders: records outside the rank window can never pass the test
 #pragma unroll
       for (int r = 0; r < PER; ++r)
@@ -119,10 +157,11 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           if (rk < first_rank || rk >= last_rank)
             s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS + 5] = __int_as_float(0x7f800000);
         }
+      if (BULK) fence_proxy_async_smem();  // these generic-proxy stores precede the bulk copy that reuses the slot
     }
-    if (__syncthreads_count(live > 0) == 0) break;
+    if (__syncthreads_count(alive()) == 0) break;
     const int count = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
-    if (__any_sync(0xFFFFFFFFu, live > 0)) {  // warp-uniform: finished lanes idle along (their pixels are parked)
+    if (__any_sync(0xFFFFFFFFu, alive())) {  // warp-uniform: finished lanes idle along (their pixels are parked)
       const float *base = s_rec[buf];
       // The list is walked four records at a time with no bound check inside the group: slots past the end of the
       // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
@@ -134,7 +173,8 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           const float2 w = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 4);  // B thr
           if (COUNT && j + u < count) {
             ++my_iters;
-            my_evals += live;
+#pragma unroll
+            for (int k = 0; k < PX; ++k) my_evals += fy[k] < 0.5f * kParkedY;
           }
           const float dx = fsub(q.x, fx);
           const float adx2 = fmul(q.z, fmul(dx, dx));
@@ -171,10 +211,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
                   C2[k] = fmaf(wgt, gbl.y, C2[k]);
                   T[k] = fmaf(-alpha, T[k], T[k]);
                   if (TRACK) last[k] = (uint32_t)b * kBatch + j + u + 1;  // only a later backward pass needs it
-                  if (T[k] < kStopT) {  // stop AFTER the blend that crosses 1e-4
-                    fy[k] = kParkedY;
-                    --live;
-                  }
+                  if (T[k] < kStopT) fy[k] = kParkedY;  // stop AFTER the blend that crosses 1e-4
                 }
               }
             }
@@ -183,12 +220,12 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
         // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
         // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
         // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
-        if (__all_sync(0xFFFFFFFFu, live == 0)) break;
+        if (!__any_sync(0xFFFFFFFFu, alive())) break;
       }
     }
     __syncthreads();  // everyone is done with s_rec[buf] before batch b+2 is gathered into it
   }
-  cp_async_wait<0>();
+  if (!BULK) cp_async_wait<0>();
 
   if (COUNT) {
     unsigned long long mx = my_iters;
@@ -243,6 +280,15 @@ __global__ void blend_one_kernel(int x0, int y0, int x1, int y1, float mx, float
 using namespace gsr;
 
 // pixels per thread of the blend kernel: 4 unless GSR_BLEND_PX=2|4|8 is set (tuning knob, read once)
+// staging path of the blend kernel: GSR_BLEND_STAGE=bulk selects cp.async.bulk + mbarrier, anything else cp.async
+static bool blend_stage_bulk() {
+  static const bool bulk = [] {
+    const char *e = getenv("GSR_BLEND_STAGE");
+    return e && e[0] == 'b';
+  }();
+  return bulk;
+}
+
 static int blend_pixels_per_thread() {
   static const int px = [] {  // function-local static: initialised once, thread-safe
     const char *e = getenv("GSR_BLEND_PX");
@@ -266,10 +312,15 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   if (first_rank == 0 && last_rank == 0xFFFFFFFFu) blend_rank = nullptr;
   dim3 grid(tg.tiles_x, tile_row_end - tile_row_begin);
   const int px = blend_pixels_per_thread();
-#define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
-  blend_kernel<PX, COUNT, RANKED, TRACK><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                              \
+  const bool bulk = blend_stage_bulk();
+#define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, BULK)                                                          \
+  blend_kernel<PX, COUNT, RANKED, TRACK, BULK><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                        \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
       blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
+#define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
+  do {                                                                                                            \
+    if (bulk && PX == 4) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, true); else GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, false); \
+  } while (0)
 #define GSR_BLEND_PICK2(PX, COUNT, RANKED)                                                                         \
   do {                                                                                                            \
     if (n_contrib) GSR_BLEND_LAUNCH(PX, COUNT, RANKED, true); else GSR_BLEND_LAUNCH(PX, COUNT, RANKED, false);      \

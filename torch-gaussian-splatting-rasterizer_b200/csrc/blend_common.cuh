@@ -22,12 +22,56 @@ __device__ __forceinline__ float blend_power(float A, float C, float B, float dx
 }
 
 // alpha = min(o*exp(power), 0.99) (:285-288) as one FFMA + MUFU.EX2.  Its VALUE may differ from the reference's by
-// a few 1e-7 (continuous, harmless); the DECISION alpha > 1/255 (:291) is discontinuous, so inside a +-1e-5 band
-// around the threshold it is re-taken with the reference's own arithmetic.  Call only when power >= thr.
-__device__ __forceinline__ bool blend_alpha(float power, float opacity, float log2_opacity, float &alpha) {
-  alpha = fminf(ex2_approx(fmaf(power, 1.4426950408889634f, log2_opacity)), kMaxDensity);
-  if (fabsf(alpha - kMinAlpha) < 3.9e-8f) alpha = fminf(fmul(opacity, expf(power)), kMaxDensity);  // 1e-5 relative
+// a few 1e-7 (continuous, harmless); the DECISION alpha > 1/255 (:291) is discontinuous, so inside a +-1e-5 (relative)
+// band around the threshold it is re-taken with the reference's own arithmetic, o * expf(power).  Call only when
+// power >= thr.
+//   fast path (everything but a thin shell at the rim of the splat): e > 1/255 + 4e-8 is above the band, so the
+//   decision is `power <= 0` and the value min(e, 0.99) - two compares, no subtraction, no second exp;
+//   band path (kept out of the hot instruction stream): the exact re-evaluation.  alpha - 1/255 is exact there
+//   (Sterbenz), so the band test means what it says.
+//   The re-evaluation uses a CORRECTLY ROUNDED exp (double exp rounded once to f32) - CUDA's expf is only good to
+//   2 ulp, and one ulp decides here: at BASELINE config 2 (2594x1681) a Gaussian with o * e^power = 1/255 + 0.2 ulp was
+//   kept by the expf version and dropped by the reference (torch's exp is correctly rounded on ~99 % of inputs), a
+//   2.3e-3 error at one pixel (profiles/r02_pixel_attribution_C2_full.json).
+constexpr float kBandHalfWidth = 3.9e-8f;
+constexpr float kBandHi = kMinAlpha + 4.0e-8f;  // any rounding of this sum (< 2.4e-10) keeps it above 1/255 + 3.9e-8
+// exp(x) rounded once to f32, for the band path (x = ln(1/(255 o)) there, i.e. -5.6 <= x <= 0; valid for |x| < 700).
+// Inline FP64 - argument reduction by ln 2 (hi + lo), degree-13 Taylor polynomial on |r| <= 0.347 (truncation 4e-18),
+// exact scaling by 2^k - instead of a call to exp(): an ABI call inside the blend loop cost 6 registers per thread.
+__device__ __forceinline__ float exp_correctly_rounded(float xf) {
+  const double x = (double)xf;
+  const double k = rint(x * 1.4426950408889634074);
+  double r = fma(k, -6.93147180369123816490e-01, x);
+  r = fma(k, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;   // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);   // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);  // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);  // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06); // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);   // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);  // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);  // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);  // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02); // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01); // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double scale = __longlong_as_double(((long long)k + 1023ll) << 52);  // 2^k, exact for -1022 <= k <= 1023
+  return (float)(p * scale);
+}
+__device__ __forceinline__ float blend_alpha_exact(float power, float opacity) {
+  return fminf(fmul(opacity, exp_correctly_rounded(power)), kMaxDensity);
+}
+__device__ __forceinline__ bool blend_alpha_band(float power, float opacity, float &alpha) {
+  if (fabsf(alpha - kMinAlpha) < kBandHalfWidth) alpha = blend_alpha_exact(power, opacity);
   return alpha > kMinAlpha && power <= 0.0f;  // :291
+}
+__device__ __forceinline__ bool blend_alpha(float power, float opacity, float log2_opacity, float &alpha) {
+  const float e = ex2_approx(fmaf(power, 1.4426950408889634f, log2_opacity));
+  alpha = fminf(e, kMaxDensity);
+  if (e > kBandHi) return power <= 0.0f;
+  return blend_alpha_band(power, opacity, alpha);
 }
 
 
@@ -92,5 +136,33 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- bulk async copies (TMA unit, UBLKCP) + mbarrier completion: the alternative staging path of the blend kernel ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_arrive(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 }  // namespace gsr

@@ -98,6 +98,21 @@ __host__ __device__ __forceinline__ TileGrid make_grid(int width, int height) {
   return g;
 }
 
+// ---- one frame's workspace, carved (api.cu) ----------------------------------------------------------------------
+struct FrameBuffers {
+  uint32_t *depth_key, *tiles_touched, *tile_span, *order, *blend_rank, *depth_hist, *tile_ranges, *tile_gids;
+  float *rec;
+  void *bin, *zero_a;
+  size_t bin_bytes, zero_a_bytes, zero_b_bytes;
+};
+int frame_buffers(int64_t n, int width, int height, int64_t max_dup, void *workspace, size_t workspace_bytes,
+                  FrameBuffers *fb);
+int frame_begin(const FrameBuffers &fb, cudaStream_t stream);
+int frame_finish(const FrameBuffers &fb, int64_t n, const gsr_camera *cam, int64_t max_dup, float *image,
+                 gsr_frame_info *info_dev, cudaStream_t stream, float *final_T = nullptr, uint32_t *n_contrib = nullptr,
+                 uint32_t first_rank = 0, uint32_t last_rank = 0xFFFFFFFFu, int32_t tile_row_begin = 0,
+                 int32_t tile_row_end = -1);
+
 // ---- stage launchers shared between translation units ------------------------------------------
 struct SortScratch {   // carved from a caller workspace
   uint32_t *hist;      // [4][256] global digit counts
@@ -118,7 +133,18 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
                       const uint32_t *ready_hist, const uint32_t *live_flags = nullptr, uint32_t *n_live_out = nullptr,
-                      bool scratch_zeroed = false);
+                      bool scratch_zeroed = false, bool adaptive = false);
+// Where an ADAPTIVE sort (launch_sort_pairs(..., adaptive = true)) left its result: 0 = (keys_tmp, values_tmp),
+// 1 = (keys_out, values_out).  hist = the digit histogram rows of all `passes` passes, n_total = number of sorted keys.
+// Called by all threads of a CTA of at least 256 threads.
+__device__ __forceinline__ int sorted_buffer_index(const uint32_t *__restrict__ hist, int passes, uint32_t n_total) {
+  int executed = 1;
+  for (int q = 1; q < passes; ++q) {
+    const uint32_t h = threadIdx.x < 256 ? __ldg(hist + q * 256 + threadIdx.x) : 0u;
+    executed += __syncthreads_or(h == n_total) == 0;
+  }
+  return (executed & 1) ? 0 : 1;
+}
 // gsr_bin with the option of a workspace whose zero-initialised head (bin_zero_bytes) the caller has already cleared
 int bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hist, const uint32_t *tiles_touched,
              const uint32_t *tile_span, int32_t width, int32_t height, int64_t max_dup, uint32_t *depth_order,

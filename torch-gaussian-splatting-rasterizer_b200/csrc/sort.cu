@@ -124,13 +124,25 @@ constexpr int kBigWarps = kBigThreads / 32;
 // clear): they are ranked in a group of their own and never stored, so the pass also compacts - the separate
 // compaction kernel (and its look-back) of the binning stage is gone.  The pass then runs over all n_host entries and
 // writes the number of survivors (the sum of the digit counts) to *n_out for the passes that follow.
+//
+// dyn_pass > 0: ADAPTIVE pass of a sort whose passes may be skipped on the device.  A pass whose digit histogram has a
+// single occupied bin is the identity permutation (all keys share the digit) - e.g. the top byte of the depth keys of a
+// scene whose depths lie within one or two binades.  Such a pass returns at once; the passes that do run ping-pong
+// between the buffers (keys_in, vals_in) = X1 and (keys_out, vals_out) = X0 in the order they actually execute, each
+// deriving its source from the histograms of the passes before it (hist points at the rows of ALL passes then).  The
+// consumer locates the result the same way (sorted_buffer_index below).  Pass 0 always runs and writes X0.
+__device__ __forceinline__ bool pass_is_identity(const uint32_t *__restrict__ hist_row, uint32_t n_total) {
+  const uint32_t h = threadIdx.x < kRadix ? __ldg(hist_row + threadIdx.x) : 0u;
+  return __syncthreads_or(h == n_total) != 0;  // one bin holds every key (called by all threads of the CTA)
+}
+
 template <int ITEMS, bool FILTER>
 __global__ void __launch_bounds__(kBigThreads, 1)
 onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
                 const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
                 uint32_t *ticket, int shift, uint32_t mask, const uint32_t *__restrict__ live_flags,
-                uint32_t *__restrict__ n_out) {
+                uint32_t *__restrict__ n_out, int dyn_pass) {
   constexpr int TILE = kBigThreads * ITEMS;
   extern __shared__ uint32_t s_dyn[];                      // s_keys[TILE] | s_vals[TILE]
   uint32_t *s_keys = s_dyn, *s_vals = s_dyn + TILE;
@@ -150,6 +162,19 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   const int64_t n = (!FILTER && n_dev) ? (int64_t)*n_dev : n_host;
   const int64_t num_tiles = (n + TILE - 1) / TILE;
   if ((int64_t)tile >= num_tiles) return;
+  if (!FILTER && dyn_pass > 0) {
+    int executed = 1;  // pass 0
+    for (int q = 1; q < dyn_pass; ++q) executed += !pass_is_identity(hist + q * kRadix, (uint32_t)n);
+    if (pass_is_identity(hist + dyn_pass * kRadix, (uint32_t)n)) return;
+    hist += dyn_pass * kRadix;
+    if (executed & 1) {  // the previous executed pass wrote X0 = (keys_out, vals_out): read it, write X1
+      const uint32_t *ki = keys_out, *vi = vals_out;
+      keys_out = const_cast<uint32_t *>(keys_in);
+      vals_out = const_cast<uint32_t *>(vals_in);
+      keys_in = ki;
+      vals_in = vi;
+    }
+  }
 
   // ---- load: warp w owns the contiguous run [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item i of lane l at i*32+l ----
   const int64_t base = (int64_t)tile * TILE + warp * (ITEMS * 32) + lane;
@@ -332,7 +357,8 @@ int sort_scratch_carve(void *workspace, size_t bytes, int64_t n, SortScratch *ou
 int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t *keys_out, uint32_t *values_out,
                       uint32_t *keys_tmp, uint32_t *values_tmp, int64_t n, const uint32_t *n_dev, int begin_bit,
                       int end_bit, const SortScratch &s, cudaStream_t stream, bool skip_final_keys,
-                      const uint32_t *ready_hist, const uint32_t *live_flags, uint32_t *n_live_out, bool scratch_zeroed) {
+                      const uint32_t *ready_hist, const uint32_t *live_flags, uint32_t *n_live_out, bool scratch_zeroed,
+                      bool adaptive) {
   GSR_REQUIRE(n >= 0 && n < (1ll << 30), "sort size out of range (must be < 2^30)");
   GSR_REQUIRE((live_flags == nullptr) == (n_live_out == nullptr), "live_flags and n_live_out go together");
   GSR_REQUIRE(!live_flags || n_dev == n_live_out, "a filtering sort counts its own survivors: n_dev must be n_live_out");
@@ -356,21 +382,37 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
                                                                  begin_bit, passes, last_mask);
     GSR_LAUNCH_CHECK();
   }
+  GSR_REQUIRE(!adaptive || live_flags, "adaptive pass skipping is implemented for filtering sorts");
   const uint32_t *kin = keys_in, *vin = values_in;
   for (int p = 0; p < passes; ++p) {
     const bool to_out = ((passes - 1 - p) % 2) == 0;
     uint32_t *kout = to_out ? keys_out : keys_tmp;
     uint32_t *vout = to_out ? values_out : values_tmp;
-    if (p == passes - 1 && skip_final_keys) kout = nullptr;  // caller only wants the permutation
+    if (p == passes - 1 && skip_final_keys && !adaptive) kout = nullptr;  // caller only wants the permutation
     const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
     const size_t smem = sizeof(uint32_t) * 2 * (size_t)kBigThreads * items;
     const bool filter = p == 0 && live_flags != nullptr;
+    const uint32_t *hist_p = hist + p * kRadix;
+    int dyn_pass = 0;
+    if (adaptive) {  // X0 = (keys_tmp, values_tmp) is what pass 0 writes, X1 = (keys_out, values_out)
+      if (p == 0) {
+        kout = keys_tmp;
+        vout = values_tmp;
+      } else {  // the kernel swaps the two when an odd number of passes ran before it
+        kin = keys_out;
+        vin = values_out;
+        kout = keys_tmp;
+        vout = values_tmp;
+        hist_p = hist;
+        dyn_pass = p;
+      }
+    }
 #define GSR_SWEEP_LAUNCH(IT, F)                                                                                   \
   do {                                                                                                            \
     GSR_CHECK_CUDA((ensure_dynamic_smem<&onesweep_kernel<IT, F>>((int)(sizeof(uint32_t) * 2 * kBigThreads * IT))));  \
     onesweep_kernel<IT, F><<<(unsigned)tiles, kBigThreads, smem, stream>>>(                                        \
-        kin, vin, kout, vout, n, n_dev, hist + p * kRadix, s.status + p * s.status_stride, s.tickets + p,          \
-        begin_bit + 8 * p, mask, live_flags, n_live_out);                                                         \
+        kin, vin, kout, vout, n, n_dev, hist_p, s.status + p * s.status_stride, s.tickets + p,                     \
+        begin_bit + 8 * p, mask, live_flags, n_live_out, dyn_pass);                                               \
   } while (0)
 #define GSR_SWEEP(IT)                                                                                             \
   case IT: {                                                                                                      \
@@ -411,5 +453,5 @@ extern "C" int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in
   int rc = sort_scratch_carve(workspace, workspace_bytes, n, &s);
   if (rc) return rc;
   return launch_sort_pairs(keys_in, values_in, keys_out, values_out, keys_tmp, values_tmp, n, n_dev, begin_bit,
-                           end_bit, s, (cudaStream_t)stream, false, nullptr, nullptr, nullptr, false);
+                           end_bit, s, (cudaStream_t)stream, false, nullptr, nullptr, nullptr, false, false);
 }

@@ -60,6 +60,11 @@ PROTOTYPES = {
     "gsr_render_views_fwd": [c_void_p, c_int64, POINTER(CameraStruct), c_int32, c_int64, POINTER(c_void_p), c_size_t,
                              c_int32, POINTER(c_void_p), c_void_p, c_int64, c_void_p],
     "gsr_render_host": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, POINTER(FrameInfo)],
+    "gsr_host_renderer_create": [c_int64, c_int32, c_int32, c_int64, c_int32, POINTER(c_void_p)],
+    "gsr_host_renderer_destroy": [c_void_p],
+    "gsr_host_renderer_submit": [c_void_p, POINTER(Gaussians), POINTER(CameraStruct), c_void_p, POINTER(c_int32)],
+    "gsr_host_renderer_wait": [c_void_p, c_int32, POINTER(FrameInfo)],
+    "gsr_host_renderer_render": [c_void_p, POINTER(Gaussians), POINTER(CameraStruct), c_void_p, POINTER(FrameInfo)],
     "gsr_preprocess_fwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gsr_sh_fwd": [c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, POINTER(c_float), c_int32,

@@ -393,6 +393,89 @@ def render_views(model: GaussianModel, intr, views, degree: int = 3, renderer: O
     return out
 
 
+def _host_struct(means, log_scales, quats, opacity_logits, sh):
+    """``gsr_gaussians`` over HOST tensors (float32; dense rows, SH planar [3,16,N]-viewed-as-[N,16,3] or dense)."""
+    keep = []
+
+    def dense(t, inner):
+        t = torch.as_tensor(t)
+        if t.dtype != torch.float32 or t.is_cuda or not t.is_contiguous():
+            t = t.detach().to("cpu", torch.float32).contiguous()
+        assert t.numel() % inner == 0
+        keep.append(t)
+        return t
+
+    xyz, ls, rot, op = dense(means, 3), dense(log_scales, 3), dense(quats, 4), dense(opacity_logits, 1).reshape(-1)
+    n = xyz.shape[0]
+    sh = torch.as_tensor(sh)
+    assert sh.dim() == 3 and tuple(sh.shape[1:]) == (16, 3), "sh must be [N,16,3]"
+    if sh.dtype != torch.float32 or sh.is_cuda or sh.stride() not in ((1, n, 16 * n), (48, 3, 1)):
+        sh = sh.detach().to("cpu", torch.float32).contiguous()
+    keep.append(sh)
+    g = _cabi.Gaussians()
+    g.n = n
+    g.xyz, g.xyz_sn, g.xyz_sc = xyz.data_ptr(), 3, 1
+    g.log_scales, g.scale_sn, g.scale_sc = ls.data_ptr(), 3, 1
+    g.rots, g.rot_sn, g.rot_sc = rot.data_ptr(), 4, 1
+    g.opacity_logit, g.opacity_sn = op.data_ptr(), 1
+    g.sh = sh.data_ptr()
+    g.sh_sn, g.sh_sk, g.sh_sc = sh.stride()
+    return g, keep
+
+
+class HostRenderer:
+    """Frames from HOST tensors through the C-level pipeline ``gsr_host_renderer`` (include/gsr_b200.h): chunked upload
+    overlapped with the per-chunk preprocess, binning + blend, image read-back on its own stream, `depth` frames in
+    flight.  ``render`` is synchronous; ``submit`` / ``wait`` pipeline consecutive frames."""
+
+    def __init__(self, n_max: int, width: int, height: int, max_dup: Optional[int] = None, depth: int = 2, device="cuda"):
+        _cabi.require_cuda()
+        self.device = torch.device(device)
+        self.n_max, self.width, self.height, self.depth = int(n_max), int(width), int(height), int(depth)
+        self.max_dup = int(max_dup if max_dup is not None else max(8 * n_max, 1 << 16))
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.call("gsr_host_renderer_create", self.n_max, self.width, self.height, self.max_dup, self.depth,
+                       ctypes.byref(self._h))
+        self._alive = {}
+
+    def close(self) -> None:
+        if self._h:
+            _cabi.call("gsr_host_renderer_destroy", self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def submit(self, means, log_scales, quats, opacity_logits, sh, cam: CameraStruct, image_host: torch.Tensor) -> int:
+        assert not image_host.is_cuda and image_host.is_contiguous() and image_host.dtype == torch.float32
+        assert tuple(image_host.shape) == (self.height, self.width, 3)
+        g, keep = _host_struct(means, log_scales, quats, opacity_logits, sh)
+        t = ctypes.c_int32()
+        _cabi.call("gsr_host_renderer_submit", self._h, ctypes.byref(g), ctypes.byref(cam), _cabi.ptr(image_host),
+                   ctypes.byref(t))
+        self._alive[t.value] = (keep, image_host)  # host buffers must outlive the frame
+        return t.value
+
+    def wait(self, ticket: int) -> Dict[str, int]:
+        info = _cabi.FrameInfo()
+        try:
+            _cabi.call("gsr_host_renderer_wait", self._h, ticket, ctypes.byref(info))
+        finally:
+            self._alive.pop(ticket, None)
+        return dict(status=info.status, n_visible=info.n_visible, n_dup=info.n_dup, n_dup_peak=info.n_dup_peak)
+
+    def render(self, means, log_scales, quats, opacity_logits, sh, cam: CameraStruct,
+               image_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if image_host is None:
+            image_host = torch.empty((self.height, self.width, 3), dtype=torch.float32).pin_memory()
+        self.wait(self.submit(means, log_scales, quats, opacity_logits, sh, cam, image_host))
+        return image_host
+
+
 class BatchRenderer:
     """A batch of views of one resident (prepared) model through ONE C-ABI call, ``gsr_render_views_fwd``: the library
     round-robins the frames over `lanes` caller-owned streams / workspaces, so consecutive frames overlap on the GPU
