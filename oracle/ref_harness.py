@@ -27,7 +27,17 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-REF_DIR = os.environ.get("GSR_REFERENCE_DIR", "/root/reference")
+def _find_reference() -> str:
+    """GSR_REFERENCE_DIR, else the read-only checkout of the build container, else the staged copy that travels to the
+    GPU box for the benchmark's reference arm (git-ignored baseline/_ref, written by __graft_entry__.build())."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("GSR_REFERENCE_DIR"), "/root/reference", os.path.join(root, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "rasterize.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_DIR = _find_reference()
 _PKG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                         "torch-gaussian-splatting-rasterizer_b200")
 
@@ -95,6 +105,57 @@ def _stable_sort():
         yield
     finally:
         torch.sort = orig
+
+
+class _StopAfter(Exception):
+    """Raised by the timing wrapper to leave the reference's loop after a bounded number of blended Gaussians."""
+
+
+def time_reference(scene_dir: str, scene_index: int = 0, scale_factor: int = 2, max_blended: Optional[int] = None,
+                   threads: Optional[int] = None) -> Dict[str, float]:
+    """Wall-clock of the unmodified reference's ``run_rasterization`` on CPU, optionally left after `max_blended`
+    calls of its own ``rasterize_gaussian`` (the loop is the whole cost and is linear in the number of blended
+    Gaussians): returns seconds before the loop (load + vectorised set-up), seconds inside it, Gaussians blended and
+    how many the loop would blend in total."""
+    import time
+
+    ref = load_reference()["rasterize"]
+    orig_blend, orig_sort, orig_set_threads = ref.rasterize_gaussian, torch.sort, torch.set_num_threads
+    st = dict(t_first=None, blended=0, blendable=None)
+
+    def sort_wrap(x, *a, **k):
+        k["stable"] = True
+        return orig_sort(x, *a, **k)
+
+    def blend_wrap(gaussian_index, bboxes, screen, screen_means, sigmas, rgb, opacity_buffer, opacity):
+        if st["t_first"] is None:
+            st["t_first"] = time.perf_counter()
+            area = (bboxes[:, 2] - bboxes[:, 0]) * (bboxes[:, 3] - bboxes[:, 1])
+            st["blendable"] = int(((area != 0) & ~(sigmas == 0).any(dim=1)).sum())  # the loop's own skip rule (:441)
+        out = orig_blend(gaussian_index, bboxes, screen, screen_means, sigmas, rgb, opacity_buffer, opacity)
+        st["blended"] += 1
+        if max_blended is not None and st["blended"] >= max_blended:
+            raise _StopAfter()
+        return out
+
+    _captured_images.clear()
+    t0 = time.perf_counter()
+    try:
+        ref.rasterize_gaussian = blend_wrap
+        torch.sort = sort_wrap
+        if threads is not None:
+            torch.set_num_threads = lambda n: orig_set_threads(threads)
+        try:
+            ref.run_rasterization.callback(input_dir=scene_dir, trained_model_path=scene_dir, output_path="",
+                                           scene_index=scene_index, scale_factor=scale_factor, generate_video=False)
+        except _StopAfter:
+            pass
+    finally:
+        ref.rasterize_gaussian, torch.sort, torch.set_num_threads = orig_blend, orig_sort, orig_set_threads
+    t1 = time.perf_counter()
+    t_first = st["t_first"] if st["t_first"] is not None else t1
+    return dict(setup_s=t_first - t0, loop_s=t1 - t_first, blended=st["blended"], blendable=st["blendable"] or 0,
+                threads=torch.get_num_threads())
 
 
 def run_reference(scene_dir: str, scene_index: int = 0, scale_factor: int = 2, stable: bool = True,

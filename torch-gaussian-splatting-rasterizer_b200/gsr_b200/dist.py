@@ -144,6 +144,21 @@ class PeerGather:
         self.handle.barrier(channel=slot)
         return self.buf[slot]
 
+    def push_to(self, frame: torch.Tensor, slot: int, consumer: int) -> torch.Tensor:
+        """Gather-to-one: copy this rank's frame into ``[slot, rank]`` of rank `consumer`'s buffer only (1 / world of the
+        all-gather's traffic - for a pipeline whose frames are consumed by one rank each, e.g. round-robin encoders),
+        then join the barrier; on `consumer`, ``view(slot)`` then holds the frames of all ranks."""
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        st = self.copy_streams[0]
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            self.peers[consumer][slot, self.rank].copy_(frame, non_blocking=True)
+        cur.wait_stream(st)
+        self.handle.barrier(channel=slot)
+        return self.buf[slot]
+
     def view(self, slot: int) -> torch.Tensor:
         return self.buf[slot]
 

@@ -581,6 +581,51 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
     return out
 
 
+class Stages:
+    """The three stages of a frame over PREALLOCATED buffers, one C-ABI call each and nothing else on the stream:
+    what the benchmark times per stage with CUDA events (the dict-returning wrappers above allocate and zero-fill their
+    outputs on every call)."""
+
+    def __init__(self, model: GaussianModel, width: int, height: int, max_dup: int):
+        _cabi.require_cuda()
+        dev, n = model.device, model.n
+        self.model, self.n, self.W, self.H, self.max_dup = model, n, width, height, int(max_dup)
+        i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+        self.depth_key, self.tiles_touched, self.tile_span = i32(max(n, 1)), i32(max(n, 1)), i32(max(n, 1), 4)
+        self.rec = torch.zeros((max(n, 1), _cabi.REC_FLOATS), dtype=torch.float32, device=dev)
+        self.depth_hist, self.order, self.blend_rank = i32(1024), i32(max(n, 1)), i32(max(n, 1))
+        self.tile_gids = i32(self.max_dup)
+        self.tile_ranges = i32(((width + 15) // 16) * ((height + 15) // 16), 2)
+        self.info = torch.zeros(8, dtype=torch.int32, device=dev)
+        need = ctypes.c_size_t()
+        _cabi.call("gsr_bin_workspace_bytes", n, width, height, self.max_dup, ctypes.byref(need))
+        self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+        self.image = torch.empty((height, width, 3), dtype=torch.float32, device=dev)
+
+    def preprocess(self, cam: CameraStruct, prepared: bool = True) -> None:
+        if prepared:
+            _cabi.call("gsr_preprocess_prepared_fwd", _cabi.ptr(self.model.prepare()), self.n, ctypes.byref(cam), 0, 1 << 30,
+                       _cabi.ptr(self.depth_key), _cabi.ptr(self.tiles_touched), _cabi.ptr(self.tile_span),
+                       _cabi.ptr(self.rec), _cabi.ptr(self.depth_hist), _cabi.stream_handle())
+        else:
+            g = self.model.c_struct()
+            _cabi.call("gsr_preprocess_fwd", ctypes.byref(g), ctypes.byref(cam), 0, 1 << 30, _cabi.ptr(self.depth_key),
+                       _cabi.ptr(self.tiles_touched), _cabi.ptr(self.tile_span), _cabi.ptr(self.rec), None, None, None,
+                       None, _cabi.ptr(self.depth_hist), _cabi.stream_handle())
+
+    def bin(self) -> None:
+        ws = _align256(self._ws)
+        _cabi.call("gsr_bin", self.n, _cabi.ptr(self.depth_key), _cabi.ptr(self.depth_hist), _cabi.ptr(self.tiles_touched),
+                   _cabi.ptr(self.tile_span), self.W, self.H, self.max_dup, _cabi.ptr(self.order), None,
+                   _cabi.ptr(self.tile_gids), _cabi.ptr(self.tile_ranges), _cabi.ptr(self.info), _cabi.ptr(ws), ws.numel(),
+                   _cabi.stream_handle())
+
+    def blend(self, count: Optional[torch.Tensor] = None) -> None:
+        _cabi.call("gsr_blend_fwd", _cabi.ptr(self.rec), _cabi.ptr(self.tile_gids), _cabi.ptr(self.tile_ranges), self.W,
+                   self.H, 0, -1, None, 0, U32_MAX, _cabi.ptr(self.image), None, None, _cabi.ptr(count),
+                   _cabi.stream_handle())
+
+
 def sort_pairs(keys: torch.Tensor, values: Optional[torch.Tensor], begin_bit: int = 0, end_bit: int = 32,
                n_dev: Optional[torch.Tensor] = None):
     _cabi.require_cuda()
