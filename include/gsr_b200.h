@@ -87,6 +87,10 @@ int gsr_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
 /* Measured FP32 FMA throughput of the current device (TFLOP/s, FMA = 2) and the SM clock it implies: the
  * denominator of the blend stage's roofline.  Synchronises; diagnostics only. */
 int gsr_fp32_fma_peak(double *tflops, double *sm_mhz_effective);
+/* Diagnostics: choose the blend kernel's staging path (0 = cp.async per CTA, 1 = cp.async.bulk + mbarrier, 2 = cp.async
+ * per warp) and the batched rejection test (0 / 1) at run time; stage < 0 returns to the built-in default (or the
+ * GSR_BLEND_STAGE / GSR_BLEND_PRETEST environment variables).  All variants produce bit-identical images. */
+int gsr_debug_blend_variant(int stage, int pretest);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole frame: rasterize.py:354-452 for one view.  image[H,W,3] is the reference's
@@ -152,7 +156,8 @@ int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t 
  *   the planar [3,16,n] block (strides 1, n, 16n - what read_color_components builds, utils.py:21-31) or dense [n,16,3].
  *   Pinned host memory gives asynchronous copies; pageable memory works but serialises.
  * submit() enqueues one frame and returns a ticket; the host buffers (inputs and image) must stay valid and unchanged
- * until wait(ticket) returns.  At most `depth` tickets are outstanding: submit() blocks on the oldest one otherwise.
+ * until wait(ticket) returns.  At most `depth` tickets may be outstanding: submit() refuses (GSR_ERR_INVALID_ARGUMENT)
+ * when the slot it would reuse has not been waited for - nothing is recycled silently, every frame's status is read.
  * wait() returns GSR_ERR_DUP_OVERFLOW (image invalid) when the frame needed more than max_dup pairs; info_host (may be
  * NULL) receives the frame's counters.  render() = submit + wait.  Not thread-safe per object. */
 typedef struct gsr_host_renderer gsr_host_renderer;

@@ -548,10 +548,18 @@ def test_host_renderer_pipeline(golden, R):
     sh_planar = torch.from_numpy(cloud.sh_planar()).pin_memory().permute(2, 1, 0)
     hr = R.HostRenderer(cloud.n, intr.width, intr.height, depth=2)
     outs = [torch.empty((intr.height, intr.width, 3)).pin_memory() for _ in cams]
-    tickets = []
-    for c, o in zip(cams, outs):           # more submissions than slots: the third blocks on the first
+    tickets, infos = [], []
+    for c, o in zip(cams, outs):           # at most `depth` frames in flight: wait for the oldest, then submit
+        if len(tickets) == 2:
+            infos.append(hr.wait(tickets.pop(0)))
         tickets.append(hr.submit(*host, sh_planar, c, o))
-    infos = [hr.wait(t) for t in tickets]
+    infos += [hr.wait(t) for t in tickets]
+    with pytest.raises(Exception):         # a ticket can be waited for once
+        hr.wait(0)
+    t0 = hr.submit(*host, sh_planar, cams[0], outs[0]); t1 = hr.submit(*host, sh_planar, cams[1], outs[1])
+    with pytest.raises(Exception):         # a third frame would recycle a slot nobody has waited for
+        hr.submit(*host, sh_planar, cams[2], outs[2])
+    hr.wait(t0); hr.wait(t1)
     for o, w, info in zip(outs, want, infos):
         assert torch.equal(o, w) and info["status"] == 0 and info["n_visible"] > 0
     sh_dense = sh_planar.contiguous().pin_memory()

@@ -25,28 +25,46 @@
 
 #include "blend_common.cuh"
 
+#ifndef GSR_DEFAULT_BLEND_STAGE
+#define GSR_DEFAULT_BLEND_STAGE 0   // kStageCta
+#endif
+#ifndef GSR_DEFAULT_BLEND_PRETEST
+#define GSR_DEFAULT_BLEND_PRETEST 0
+#endif
+
 namespace gsr {
 
 constexpr float kParkedY = 1e18f;
 
-// BULK selects how a batch of records reaches shared memory:
-//   false  cp.async (LDGSTS): every thread gathers its records with three 16-byte asynchronous copies, completion by
-//          cp.async.wait_group + the batch barrier;
-//   true   cp.async.bulk (the TMA unit, SASS UBLKCP): one 48-byte bulk copy per record, completion counted in bytes
-//          by an mbarrier (expect_tx / complete_tx) that the consumers wait on - no wait_group.
-// Both deliver the same bytes to the same slots; the image is bit-identical (tests/test_gpu_edges.py).  Which one is
-// the default is a measurement (profiles/r02_notes.md): the lists are GATHERS of scattered 48-byte records, so the
-// bulk path needs one TMA operation per record, issued from uniform registers one lane at a time.
-template <int PX, bool COUNT, bool RANKED, bool TRACK, bool BULK>
+// STAGE selects how a batch of records reaches shared memory:
+//   kStageCta   cp.async (LDGSTS), one double buffer per CTA: every thread gathers its share of a 128-record batch with
+//               three 16-byte asynchronous copies; completion by cp.async.wait_group + the batch barrier;
+//   kStageBulk  cp.async.bulk (the TMA unit, SASS UBLKCP): one 48-byte bulk copy per record, completion counted in
+//               bytes by an mbarrier (expect_tx / complete_tx) that the consumers wait on - no wait_group;
+//   kStageWarp  cp.async, one double buffer per WARP (64-record batches): the two warps of a tile never meet at a
+//               barrier - each gathers the list for itself (the second read of a record hits L2), walks it at its own
+//               pace and leaves when its 128 pixels are done.
+// All deliver the same bytes in the same order; the image is bit-identical (tests/test_gpu_edges.py).  Which one is the
+// default is a measurement (profiles/r02_notes.md): the lists are GATHERS of scattered 48-byte records, so the bulk path
+// needs one TMA operation per record, issued from uniform registers one lane at a time.
+// PRETEST: the rejection tests of a group of four records are evaluated back to back (16 independent power
+// evaluations, no branch between them) before any of the four is blended.
+constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2;
+
+template <int PX, bool COUNT, bool RANKED, bool TRACK, int STAGE, bool PRETEST>
 __global__ void __launch_bounds__(256 / PX)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
              uint32_t *__restrict__ n_contrib, gsr_frame_info *info, float neg_zero) {
+  constexpr bool BULK = STAGE == kStageBulk, SOLO = STAGE == kStageWarp;
   constexpr int THREADS = 256 / PX;
-  constexpr int kBatch = PX >= 8 ? 64 : 128;  // records per staged batch (smaller CTAs keep more CTAs resident)
-  constexpr int PER = kBatch / THREADS;  // records gathered per thread and batch
-  __shared__ __align__(128) float s_rec[2][kBatch * GSR_REC_FLOATS];
+  constexpr int WARPS = THREADS / 32;
+  constexpr int kBatch = SOLO ? 64 : (PX >= 8 ? 64 : 128);  // records per staged batch
+  constexpr int GATHERERS = SOLO ? 32 : THREADS;            // threads that share the gather of one batch
+  constexpr int PER = kBatch / GATHERERS;                   // records gathered per thread and batch
+  constexpr int BUFS = SOLO ? 2 * WARPS : 2;
+  __shared__ __align__(128) float s_rec[BUFS][kBatch * GSR_REC_FLOATS];
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x;
@@ -57,6 +75,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   constexpr int R = GSR_TILE / PX;            // rows per slot block
   constexpr int COLS = 32 / R;                // columns per warp
   const int lane = tid & 31, warp = tid >> 5;
+  const int gtid = SOLO ? lane : tid;         // index among the threads that gather a batch together
   const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
   const int py0 = tile_y * GSR_TILE + (lane / COLS);
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
@@ -94,11 +113,12 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     }
     __syncthreads();
   }
+  float *const my_bufs = SOLO ? &s_rec[2 * warp][0] : &s_rec[0][0];  // this thread's double buffer
   uint32_t gnext[PER];
   auto load_ids = [&](int b) {
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
-      const uint32_t idx = range.x + (uint32_t)b * kBatch + r * THREADS + tid;
+      const uint32_t idx = range.x + (uint32_t)b * kBatch + r * GATHERERS + gtid;
       gnext[r] = (b < num_batches && idx < range.y) ? __ldg(gids + idx) : 0xFFFFFFFFu;
     }
   };
@@ -112,7 +132,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     }
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
-      float *dst = &s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS];
+      float *dst = my_bufs + buf * (kBatch * GSR_REC_FLOATS) + (r * GATHERERS + gtid) * GSR_REC_FLOATS;
       if (gnext[r] != 0xFFFFFFFFu) {
         const float4 *src = rec + (size_t)gnext[r] * 3;
         if (BULK) {
@@ -128,6 +148,100 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     }
     if (!BULK) cp_async_commit();
   };
+
+  // one pixel slot of one record: alpha, keep decision, blend (rasterize.py:285-303)
+  auto blend_slot = [&](int k, float power, float opacity, float log2o, float cr, float cg, float cb, uint32_t pos) {
+    float alpha;
+    if (blend_alpha(power, opacity, log2o, alpha)) {
+      const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
+      C0[k] = fmaf(wgt, cr, C0[k]);
+      C1[k] = fmaf(wgt, cg, C1[k]);
+      C2[k] = fmaf(wgt, cb, C2[k]);
+      T[k] = fmaf(-alpha, T[k], T[k]);
+      if (TRACK) last[k] = pos;                // only a later backward pass needs it
+      if (T[k] < kStopT) fy[k] = kParkedY;     // stop AFTER the blend that crosses 1e-4
+    }
+  };
+  auto powers = [&](const float *r, float power[PX], float &thr) -> bool {
+    const float4 q = *reinterpret_cast<const float4 *>(r);      // mx my A C
+    const float2 w = *reinterpret_cast<const float2 *>(r + 4);  // B thr
+    const float dx = fsub(q.x, fx);
+    const float adx2 = fmul(q.z, fmul(dx, dx));
+    const float bdx = fmul(w.x, dx);
+    bool any = false;
+    if (PX == 4) {
+      // the four pixels as two packed pairs: 6 FADD2/FMUL2/FFMA2 per pair instead of 12 scalar operations, every
+      // half rounded like the scalar code (blend_common.cuh)
+      float dy[4];
+      blend_power4(q.y, q.w, adx2, bdx, fy, neg_zero2, dy, power);
+#pragma unroll
+      for (int k = 0; k < PX; ++k) any |= power[k] >= w.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < PX; ++k) {
+        const float dy = fsub(q.y, fy[k]);
+        // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
+        power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
+        any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
+      }
+    }
+    thr = w.y;
+    return any;
+  };
+  // walk one staged batch; returns when the batch is consumed or the whole warp has terminated
+  auto eval_batch = [&](const float *base, int count, uint32_t list_base) {
+    // The list is walked four records at a time with no bound check inside the group: slots past the end of the
+    // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
+    const int count4 = (count + 3) & ~3;
+    for (int j = 0; j < count4; j += 4) {
+      if (COUNT) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u < count) {
+            ++my_iters;
+#pragma unroll
+            for (int k = 0; k < PX; ++k) my_evals += fy[k] < 0.5f * kParkedY;
+          }
+      }
+      if (PRETEST) {
+        float pw[4][PX], thr[4];
+        bool any[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) any[u] = powers(base + (j + u) * GSR_REC_FLOATS, pw[u], thr[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (any[u]) {
+            const float *r = base + (j + u) * GSR_REC_FLOATS;
+            const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
+            const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
+#pragma unroll
+            for (int k = 0; k < PX; ++k)  // the powers were taken before the group: a pixel an earlier record of the
+              //                             group terminated must not blend (T < 1e-4 only after a terminating blend)
+              if (pw[u][k] >= thr[u] && T[k] >= kStopT)
+                blend_slot(k, pw[u][k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float *r = base + (j + u) * GSR_REC_FLOATS;
+          float power[PX], thr;
+          if (powers(r, power, thr)) {
+            const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
+            const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+              if (power[k] >= thr) blend_slot(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
+          }
+        }
+      }
+      // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
+      // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
+      // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
+      if (!__any_sync(0xFFFFFFFFu, alive())) break;
+    }
+  };
+
   load_ids(0);
   issue(0, 0);
   uint32_t gcur[PER];
@@ -149,81 +263,29 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     } else {
       cp_async_wait<1>();  // batch b has landed for this thread's copies
     }
+    float *const cur = my_bufs + buf * (kBatch * GSR_REC_FLOATS);
     if (RANKED) {        // progressive renders: records outside the rank window can never pass the test
 #pragma unroll
       for (int r = 0; r < PER; ++r)
         if (gmine[r] != 0xFFFFFFFFu) {
           const uint32_t rk = __ldg(blend_rank + gmine[r]);
           if (rk < first_rank || rk >= last_rank)
-            s_rec[buf][(r * THREADS + tid) * GSR_REC_FLOATS + 5] = __int_as_float(0x7f800000);
+            cur[(r * GATHERERS + gtid) * GSR_REC_FLOATS + 5] = __int_as_float(0x7f800000);
         }
       if (BULK) fence_proxy_async_smem();  // these generic-proxy stores precede the bulk copy that reuses the slot
     }
-    if (__syncthreads_count(alive()) == 0) break;
     const int count = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
-    if (__any_sync(0xFFFFFFFFu, alive())) {  // warp-uniform: finished lanes idle along (their pixels are parked)
-      const float *base = s_rec[buf];
-      // The list is walked four records at a time with no bound check inside the group: slots past the end of the
-      // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
-      const int count4 = (count + 3) & ~3;
-      for (int j = 0; j < count4; j += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 q = *reinterpret_cast<const float4 *>(base + (j + u) * GSR_REC_FLOATS);      // mx my A C
-          const float2 w = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 4);  // B thr
-          if (COUNT && j + u < count) {
-            ++my_iters;
-#pragma unroll
-            for (int k = 0; k < PX; ++k) my_evals += fy[k] < 0.5f * kParkedY;
-          }
-          const float dx = fsub(q.x, fx);
-          const float adx2 = fmul(q.z, fmul(dx, dx));
-          const float bdx = fmul(w.x, dx);
-          float power[PX];
-          bool any = false;
-          if (PX == 4) {
-            // the four pixels as two packed pairs: 6 FADD2/FMUL2/FFMA2 per pair instead of 12 scalar operations, every
-            // half rounded like the scalar code (blend_common.cuh)
-            float dy[4];
-            blend_power4(q.y, q.w, adx2, bdx, fy, neg_zero2, dy, power);
-#pragma unroll
-            for (int k = 0; k < PX; ++k) any |= power[k] >= w.y;
-          } else {
-#pragma unroll
-            for (int k = 0; k < PX; ++k) {
-              const float dy = fsub(q.y, fy[k]);
-              // (A dx^2 + C dy^2) + (B dx) dy == -0.5 (a dx^2 + c dy^2) - (b dx) dy of rasterize.py:280-283, bit for bit
-              power[k] = fadd(fadd(adx2, fmul(q.w, fmul(dy, dy))), fmul(bdx, dy));
-              any |= power[k] >= w.y;  // below thr alpha = o*exp(power) cannot exceed 1/255
-            }
-          }
-          if (any) {
-            const float2 orr = *reinterpret_cast<const float2 *>(base + (j + u) * GSR_REC_FLOATS + 6);  // opacity r
-            const float4 gbl = *reinterpret_cast<const float4 *>(base + (j + u) * GSR_REC_FLOATS + 8);  // g b log2(opacity) .
-#pragma unroll
-            for (int k = 0; k < PX; ++k) {
-              if (power[k] >= w.y) {
-                float alpha;
-                if (blend_alpha(power[k], orr.x, gbl.z, alpha)) {
-                  const float wgt = alpha * T[k];          // C += (alpha*rgb)*T, T *= (1-alpha)   (:295-303)
-                  C0[k] = fmaf(wgt, orr.y, C0[k]);
-                  C1[k] = fmaf(wgt, gbl.x, C1[k]);
-                  C2[k] = fmaf(wgt, gbl.y, C2[k]);
-                  T[k] = fmaf(-alpha, T[k], T[k]);
-                  if (TRACK) last[k] = (uint32_t)b * kBatch + j + u + 1;  // only a later backward pass needs it
-                  if (T[k] < kStopT) fy[k] = kParkedY;  // stop AFTER the blend that crosses 1e-4
-                }
-              }
-            }
-          }
-        }
-        // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
-        // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
-        // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
-        if (!__any_sync(0xFFFFFFFFu, alive())) break;
-      }
+    if (SOLO) {
+      __syncwarp();  // the lanes' copies (and sentinel / rank stores) of batch b are visible to the whole warp
+      if (!__any_sync(0xFFFFFFFFu, alive())) break;
+      eval_batch(cur, count, (uint32_t)b * kBatch);
+      __syncwarp();  // the warp is done with this buffer before batch b+2 is gathered into it
+    } else {
+      if (__syncthreads_count(alive()) == 0) break;
+      if (__any_sync(0xFFFFFFFFu, alive()))  // warp-uniform: finished lanes idle along (their pixels are parked)
+        eval_batch(cur, count, (uint32_t)b * kBatch);
+      __syncthreads();  // everyone is done with s_rec[buf] before batch b+2 is gathered into it
     }
-    __syncthreads();  // everyone is done with s_rec[buf] before batch b+2 is gathered into it
   }
   if (!BULK) cp_async_wait<0>();
 
@@ -280,13 +342,23 @@ __global__ void blend_one_kernel(int x0, int y0, int x1, int y1, float mx, float
 using namespace gsr;
 
 // pixels per thread of the blend kernel: 4 unless GSR_BLEND_PX=2|4|8 is set (tuning knob, read once)
-// staging path of the blend kernel: GSR_BLEND_STAGE=bulk selects cp.async.bulk + mbarrier, anything else cp.async
-static bool blend_stage_bulk() {
-  static const bool bulk = [] {
+// Kernel variant: GSR_BLEND_STAGE = cta | bulk | warp selects the staging path, GSR_BLEND_PRETEST = 0 | 1 the batched
+// rejection test; gsr_debug_blend_variant() overrides both at run time (profiling scripts compare them in one process).
+static int g_blend_variant = -1;  // -1: from the environment; else stage + 4 * pretest
+static int blend_variant() {
+  static const int from_env = [] {
     const char *e = getenv("GSR_BLEND_STAGE");
-    return e && e[0] == 'b';
+    const char *p = getenv("GSR_BLEND_PRETEST");
+    int stage = GSR_DEFAULT_BLEND_STAGE;
+    if (e) stage = e[0] == 'b' ? kStageBulk : (e[0] == 'w' ? kStageWarp : kStageCta);
+    const int pre = p ? (atoi(p) != 0) : GSR_DEFAULT_BLEND_PRETEST;
+    return stage + 4 * pre;
   }();
-  return bulk;
+  return g_blend_variant >= 0 ? g_blend_variant : from_env;
+}
+extern "C" int gsr_debug_blend_variant(int stage, int pretest) {
+  g_blend_variant = (stage < 0) ? -1 : (stage % 3) + 4 * (pretest != 0);
+  return GSR_OK;
 }
 
 static int blend_pixels_per_thread() {
@@ -312,14 +384,21 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   if (first_rank == 0 && last_rank == 0xFFFFFFFFu) blend_rank = nullptr;
   dim3 grid(tg.tiles_x, tile_row_end - tile_row_begin);
   const int px = blend_pixels_per_thread();
-  const bool bulk = blend_stage_bulk();
-#define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, BULK)                                                          \
-  blend_kernel<PX, COUNT, RANKED, TRACK, BULK><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                        \
+  const int variant = blend_variant();
+  const int stage_sel = variant & 3;
+  const bool pretest = (variant >> 2) & 1;
+#define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, STAGE, PRE)                                                     \
+  blend_kernel<PX, COUNT, RANKED, TRACK, STAGE, PRE><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                   \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
       blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
 #define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
   do {                                                                                                            \
-    if (bulk && PX == 4) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, true); else GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, false); \
+    if (PX != 4) GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, kStageCta, false);                                     \
+    else if (stage_sel == kStageBulk) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageBulk, false);                \
+    else if (stage_sel == kStageWarp && pretest) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp, true);      \
+    else if (stage_sel == kStageWarp) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp, false);                \
+    else if (pretest) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta, true);                                  \
+    else GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta, false);                                              \
   } while (0)
 #define GSR_BLEND_PICK2(PX, COUNT, RANKED)                                                                         \
   do {                                                                                                            \

@@ -144,10 +144,9 @@ extern "C" int gsr_host_renderer_submit(gsr_host_renderer *h, const gsr_gaussian
   GSR_CHECK_CUDA(cudaSetDevice(h->device));
   const int32_t t = h->next_ticket;
   HostSlot &sl = h->slot[t % h->depth];
-  if (sl.busy) {  // the frame that used this slot `depth` submissions ago must have been waited for, or is waited for here
-    GSR_CHECK_CUDA(cudaEventSynchronize(sl.done));
-    sl.busy = false;
-  }
+  // the frame that used this slot `depth` submissions ago must have been waited for: recycling it silently would lose
+  // its status (an overflowed frame would go unnoticed)
+  GSR_REQUIRE(!sl.busy, "all `depth` frames are in flight: gsr_host_renderer_wait() for the oldest ticket first");
   const size_t img_bytes = sizeof(float) * 3 * (size_t)h->width * h->height;
   const int64_t n1 = n > 0 ? n : 1;
   float *d_xyz = sl.d_params, *d_sc = d_xyz + pad4(3 * n1), *d_rot = d_sc + pad4(3 * n1), *d_op = d_rot + pad4(4 * n1),

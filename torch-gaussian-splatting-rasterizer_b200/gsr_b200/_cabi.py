@@ -48,6 +48,7 @@ PROTOTYPES = {
     "gsr_abi_version": [],
     "gsr_device_info": [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)],
     "gsr_fp32_fma_peak": [POINTER(ctypes.c_double), POINTER(ctypes.c_double)],
+    "gsr_debug_blend_variant": [c_int, c_int],
     "gsr_render_workspace_bytes": [c_int64, c_int32, c_int32, c_int64, POINTER(c_size_t)],
     "gsr_render_fwd": [POINTER(Gaussians), POINTER(CameraStruct), c_int64, c_void_p, c_size_t, c_void_p, c_void_p,
                        c_void_p, c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p],
