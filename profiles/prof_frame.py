@@ -1,7 +1,7 @@
 """One frame of config C3 stage by stage, for ncu (run on the GPU box):
 
     python profiles/prof_frame.py && \
-    ncu --set full --clock-control none --import-source on -k regex:gsr -s 31 -c 11 -o gpurun_out/r02_frame python profiles/prof_frame.py
+    ncu --set full --clock-control none --import-source on -k regex:"^(blend|onesweep|prepare|preprocess|scan_emit|tile_ranges)" -s 31 -c 11 -o gpurun_out/r02_frame python profiles/prof_frame.py
 
 Launch order of OUR kernels (-k regex:gsr): prepare (1), one checked frame (10), two warm-up frames (20), then the
 captured ones: gsr_prepare again (1) and one frame (10): preprocess, 4 depth-sort passes, scan+emit, 2 tile-sort passes,

@@ -26,7 +26,7 @@
 #include "blend_common.cuh"
 
 #ifndef GSR_DEFAULT_BLEND_STAGE
-#define GSR_DEFAULT_BLEND_STAGE 0   // kStageCta
+#define GSR_DEFAULT_BLEND_STAGE 2   // kStageWarp: measured fastest (profiles/r02_blend_variants_C3.json)
 #endif
 #ifndef GSR_DEFAULT_BLEND_PRETEST
 #define GSR_DEFAULT_BLEND_PRETEST 0
