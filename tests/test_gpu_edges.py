@@ -165,3 +165,30 @@ def test_packed_fp32_blend_is_bit_identical_to_the_scalar_kernel(tmp_path):
         out[px] = np.load(path)
     assert out["4"].max() > 0.1
     assert np.array_equal(out["2"].view(np.uint32), out["4"].view(np.uint32))
+
+
+def test_blend_staging_variants_are_bit_identical():
+    """cp.async per CTA, cp.async.bulk + mbarrier (TMA unit), cp.async per warp, one CTA per half tile: same records in
+    the same order, so the same image bit for bit - also with contributor tracking and a rank window."""
+    from gsr_b200 import _cabi, render as R
+
+    cloud = scenes.synth_v1(60_000, 17, scale_factor=0.45)
+    intr = scenes.Intrinsics.synthetic(389, 251)
+    cam = camera.camera_for(intr, scenes.orbit_views(1, total=9, first=2)[0], 3)
+    model = R.GaussianModel.from_cloud(cloud)
+    pre = R.preprocess(model, cam)
+    n_pairs = int((pre["tiles_touched"] & 0x7FFFFFFF).sum().item())
+    binned = R.bin_tiles(pre, cam.width, cam.height, n_pairs + 1024)
+    outs = []
+    try:
+        for stage in (0, 1, 2, 3):
+            _cabi.call("gsr_debug_blend_variant", stage, 0)
+            a = R.blend(pre, binned, cam.width, cam.height)                              # tracked
+            b = R.blend(pre, binned, cam.width, cam.height, track=False, last_rank=777)   # rank window
+            outs.append((a["image"].clone(), a["final_T"].clone(), a["n_contrib"].clone(), b["image"].clone()))
+    finally:
+        _cabi.call("gsr_debug_blend_variant", -1, 0)
+    assert outs[0][0].max() > 0.1 and not torch.equal(outs[0][0], outs[0][3])
+    for o in outs[1:]:
+        for x, y in zip(o, outs[0]):
+            assert torch.equal(x, y)

@@ -28,9 +28,6 @@
 #ifndef GSR_DEFAULT_BLEND_STAGE
 #define GSR_DEFAULT_BLEND_STAGE 2   // kStageWarp: measured fastest (profiles/r02_blend_variants_C3.json)
 #endif
-#ifndef GSR_DEFAULT_BLEND_PRETEST
-#define GSR_DEFAULT_BLEND_PRETEST 0
-#endif
 
 namespace gsr {
 
@@ -47,18 +44,22 @@ constexpr float kParkedY = 1e18f;
 // All deliver the same bytes in the same order; the image is bit-identical (tests/test_gpu_edges.py).  Which one is the
 // default is a measurement (profiles/r02_notes.md): the lists are GATHERS of scattered 48-byte records, so the bulk path
 // needs one TMA operation per record, issued from uniform registers one lane at a time.
-// PRETEST: the rejection tests of a group of four records are evaluated back to back (16 independent power
-// evaluations, no branch between them) before any of the four is blended.
-constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2;
+// (A fourth variant - the rejection tests of a group of four records evaluated back to back before any of the four is
+// blended, for instruction-level parallelism - needed 80 registers and measured 0.47-0.48 ms against 0.40-0.42; it was
+// removed after the measurement, profiles/r02_blend_variants_C3.json.)
+//   kStageHalf  kStageWarp with one CTA per WARP (32 threads, two CTAs per tile): a warp that has finished its half tile
+//               frees its slot at once instead of waiting for the tile's other warp.
+constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2, kStageHalf = 3;
 
-template <int PX, bool COUNT, bool RANKED, bool TRACK, int STAGE, bool PRETEST>
-__global__ void __launch_bounds__(256 / PX)
+template <int PX, bool COUNT, bool RANKED, bool TRACK, int STAGE>
+__global__ void __launch_bounds__(STAGE == kStageHalf ? 32 : 256 / PX,
+                                  (PX == 4 && !GSR_BAND_INLINE) ? (STAGE == kStageHalf ? 32 : 18) : 1)  // <= 56 / 64 registers
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
              uint32_t *__restrict__ n_contrib, gsr_frame_info *info, float neg_zero) {
-  constexpr bool BULK = STAGE == kStageBulk, SOLO = STAGE == kStageWarp;
-  constexpr int THREADS = 256 / PX;
+  constexpr bool BULK = STAGE == kStageBulk, HALF = STAGE == kStageHalf, SOLO = STAGE == kStageWarp || HALF;
+  constexpr int THREADS = HALF ? 32 : 256 / PX;
   constexpr int WARPS = THREADS / 32;
   constexpr int kBatch = SOLO ? 64 : (PX >= 8 ? 64 : 128);  // records per staged batch
   constexpr int GATHERERS = SOLO ? 32 : THREADS;            // threads that share the gather of one batch
@@ -68,13 +69,13 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x;
-  const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
+  const int tile_x = HALF ? blockIdx.x >> 1 : blockIdx.x, tile_y = blockIdx.y + row_begin;
   // Lane -> pixel map: a warp owns 8 columns x 16 rows of the tile... a thread owns ONE column (dx is shared by its PX
   // pixels) and the rows r, r+R, r+2R, ... with R = 16/PX, so that pixel slot k of the warp is the compact 8 x R block
   // of rows kR..kR+R-1: a Gaussian reaches few slots, and a slot whose 32 pixels all fail the test costs nothing.
   constexpr int R = GSR_TILE / PX;            // rows per slot block
   constexpr int COLS = 32 / R;                // columns per warp
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = HALF ? (blockIdx.x & 1) : tid >> 5;  // `warp` = which half of the tile
   const int gtid = SOLO ? lane : tid;         // index among the threads that gather a batch together
   const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
   const int py0 = tile_y * GSR_TILE + (lane / COLS);
@@ -113,7 +114,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     }
     __syncthreads();
   }
-  float *const my_bufs = SOLO ? &s_rec[2 * warp][0] : &s_rec[0][0];  // this thread's double buffer
+  float *const my_bufs = (SOLO && !HALF) ? &s_rec[2 * warp][0] : &s_rec[0][0];  // this thread's double buffer
   uint32_t gnext[PER];
   auto load_ids = [&](int b) {
 #pragma unroll
@@ -203,36 +204,16 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
             for (int k = 0; k < PX; ++k) my_evals += fy[k] < 0.5f * kParkedY;
           }
       }
-      if (PRETEST) {
-        float pw[4][PX], thr[4];
-        bool any[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) any[u] = powers(base + (j + u) * GSR_REC_FLOATS, pw[u], thr[u]);
+      for (int u = 0; u < 4; ++u) {
+        const float *r = base + (j + u) * GSR_REC_FLOATS;
+        float power[PX], thr;
+        if (powers(r, power, thr)) {
+          const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
+          const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (any[u]) {
-            const float *r = base + (j + u) * GSR_REC_FLOATS;
-            const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
-            const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
-#pragma unroll
-            for (int k = 0; k < PX; ++k)  // the powers were taken before the group: a pixel an earlier record of the
-              //                             group terminated must not blend (T < 1e-4 only after a terminating blend)
-              if (pw[u][k] >= thr[u] && T[k] >= kStopT)
-                blend_slot(k, pw[u][k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float *r = base + (j + u) * GSR_REC_FLOATS;
-          float power[PX], thr;
-          if (powers(r, power, thr)) {
-            const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
-            const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-              if (power[k] >= thr) blend_slot(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
-          }
+          for (int k = 0; k < PX; ++k)
+            if (power[k] >= thr) blend_slot(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
         }
       }
       // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
@@ -342,22 +323,21 @@ __global__ void blend_one_kernel(int x0, int y0, int x1, int y1, float mx, float
 using namespace gsr;
 
 // pixels per thread of the blend kernel: 4 unless GSR_BLEND_PX=2|4|8 is set (tuning knob, read once)
-// Kernel variant: GSR_BLEND_STAGE = cta | bulk | warp selects the staging path, GSR_BLEND_PRETEST = 0 | 1 the batched
-// rejection test; gsr_debug_blend_variant() overrides both at run time (profiling scripts compare them in one process).
-static int g_blend_variant = -1;  // -1: from the environment; else stage + 4 * pretest
+// Kernel variant: GSR_BLEND_STAGE = cta | bulk | warp selects the staging path; gsr_debug_blend_variant() overrides it at
+// run time (profiling scripts compare the variants in one process).
+static int g_blend_variant = -1;  // -1: from the environment; else the stage
 static int blend_variant() {
   static const int from_env = [] {
     const char *e = getenv("GSR_BLEND_STAGE");
-    const char *p = getenv("GSR_BLEND_PRETEST");
     int stage = GSR_DEFAULT_BLEND_STAGE;
-    if (e) stage = e[0] == 'b' ? kStageBulk : (e[0] == 'w' ? kStageWarp : kStageCta);
-    const int pre = p ? (atoi(p) != 0) : GSR_DEFAULT_BLEND_PRETEST;
-    return stage + 4 * pre;
+    if (e) stage = e[0] == 'b' ? kStageBulk : (e[0] == 'w' ? kStageWarp : (e[0] == 'h' ? kStageHalf : kStageCta));
+    return stage;
   }();
   return g_blend_variant >= 0 ? g_blend_variant : from_env;
 }
 extern "C" int gsr_debug_blend_variant(int stage, int pretest) {
-  g_blend_variant = (stage < 0) ? -1 : (stage % 3) + 4 * (pretest != 0);
+  (void)pretest;  // the batched rejection test was measured and removed (kept in the signature for ABI stability)
+  g_blend_variant = (stage < 0) ? -1 : (stage & 3);
   return GSR_OK;
 }
 
@@ -386,19 +366,18 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   const int px = blend_pixels_per_thread();
   const int variant = blend_variant();
   const int stage_sel = variant & 3;
-  const bool pretest = (variant >> 2) & 1;
-#define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, STAGE, PRE)                                                     \
-  blend_kernel<PX, COUNT, RANKED, TRACK, STAGE, PRE><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                   \
+#define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, STAGE)                                                          \
+  blend_kernel<PX, COUNT, RANKED, TRACK, STAGE><<<(STAGE == kStageHalf ? dim3(grid.x * 2, grid.y) : grid),             \
+                                                  (STAGE == kStageHalf ? 32 : 256 / PX), 0, (cudaStream_t)stream>>>(   \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
       blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
 #define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
   do {                                                                                                            \
-    if (PX != 4) GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, kStageCta, false);                                     \
-    else if (stage_sel == kStageBulk) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageBulk, false);                \
-    else if (stage_sel == kStageWarp && pretest) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp, true);      \
-    else if (stage_sel == kStageWarp) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp, false);                \
-    else if (pretest) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta, true);                                  \
-    else GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta, false);                                              \
+    if (PX != 4) GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, kStageCta);                                            \
+    else if (stage_sel == kStageBulk) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageBulk);                       \
+    else if (stage_sel == kStageWarp) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp);                       \
+    else if (stage_sel == kStageHalf) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageHalf);                       \
+    else GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta);                                                     \
   } while (0)
 #define GSR_BLEND_PICK2(PX, COUNT, RANKED)                                                                         \
   do {                                                                                                            \

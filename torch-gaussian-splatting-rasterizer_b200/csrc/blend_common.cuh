@@ -60,7 +60,17 @@ __device__ __forceinline__ float exp_correctly_rounded(float xf) {
   const double scale = __longlong_as_double(((long long)k + 1023ll) << 52);  // 2^k, exact for -1022 <= k <= 1023
   return (float)(p * scale);
 }
+// Out of line on purpose: inlined, the sixteen copies (4 records x 4 pixel slots) of the FP64 polynomial made the blend
+// loop 1720 instructions instead of 1008 (instruction-fetch stalls); the call costs nothing where it matters because
+// the band is reached by about one evaluation in 10^5.  -DGSR_BAND_INLINE=1 restores the inlined form (A/B builds).
+#ifndef GSR_BAND_INLINE
+#define GSR_BAND_INLINE 0
+#endif
+#if GSR_BAND_INLINE
 __device__ __forceinline__ float blend_alpha_exact(float power, float opacity) {
+#else
+static __device__ __noinline__ float blend_alpha_exact(float power, float opacity) {
+#endif
   return fminf(fmul(opacity, exp_correctly_rounded(power)), kMaxDensity);
 }
 __device__ __forceinline__ bool blend_alpha_band(float power, float opacity, float &alpha) {

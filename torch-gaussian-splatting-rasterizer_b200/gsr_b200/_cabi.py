@@ -12,7 +12,7 @@ from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c
 from .camera import CameraStruct
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG, "csrc", "libgsr_b200.so")
+LIB_PATH = os.environ.get("GSR_B200_LIB") or os.path.join(PKG, "csrc", "libgsr_b200.so")  # override: A/B builds only
 
 GSR_OK, GSR_ERR_INVALID_ARGUMENT, GSR_ERR_CUDA, GSR_ERR_WORKSPACE_TOO_SMALL, GSR_ERR_DUP_OVERFLOW = range(5)
 REC_FLOATS = 12
