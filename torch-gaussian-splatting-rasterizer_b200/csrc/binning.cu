@@ -134,14 +134,67 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
     if (w < warp) pre += s_warp[w];
     total += s_warp[w];
   }
-  // decoupled look-back by warp 0, 32 predecessors per round trip (lane l inspects CTA tile-1-l of the window);
-  // the exclusive prefix is broadcast through shared memory
+  // Order of business: (1) warp 0 PUBLISHES this CTA's aggregate at once, so that no successor waits for it longer than
+  // necessary; (2) every warp expands its pairs into shared-memory staging - that needs only CTA-relative offsets;
+  // (3) warp 0 walks back over its predecessors (decoupled look-back, 32 per round trip: lane l inspects CTA
+  // tile-1-l of the window) - by now most of them have published, and the other warps were expanding instead of
+  // waiting at a barrier (ncu on the previous order: 6.4 barrier-stall cycles per issue); (4) coalesced stores.
+  if (warp == 0 && lane == 0)
+    st_volatile_u64(status + tile, (tile == 0 ? kScanInclusive : kScanAggregate) | total);
+  // ---- emission.  The 128 Gaussians of a warp own one contiguous output range.  Every lane expands ITS Gaussians
+  //      (a walk over the set bits of the keep mask: a few instructions per pair) into the warp's staging buffer in
+  //      shared memory, at the offset its prefix gives; the warp then copies the buffer out with coalesced 128-byte
+  //      stores.  A staged pair is one word, tile << 7 | slot of the Gaussian in the warp.  (A first version let
+  //      every lane binary-search the owner of each output element: ~170 thread instructions per pair.)  Warps whose
+  //      range exceeds the buffer - a few huge splats - fall back to that search, element by element.
+  uint32_t *stage = s_dyn + (size_t)warp * kStageWords;
+  uint32_t *s_gid = stage + kStageCap;
+  uint32_t *s_off = s_gid + 32 * kScanItems;
+  const unsigned long long thread_rel = pre + inc - mine;  // pairs of this CTA before this thread's first Gaussian
+  const unsigned long long warp_rel = __shfl_sync(0xFFFFFFFFu, thread_rel, 0);
+  const unsigned long long warp_total = __shfl_sync(0xFFFFFFFFu, thread_rel + mine, 31) - warp_rel;
+  const bool staged = warp_total != 0 && warp_total <= (unsigned long long)kStageCap;
+  if (blend_rank) {  // every entry of the compacted order is blended: its rank is its position
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+      if (gid[j] != 0xFFFFFFFFu) blend_rank[gid[j]] = (uint32_t)(first + j);
+  }
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) s_gid[lane * kScanItems + j] = gid[j];
+  if (staged) {
+    uint32_t off = (uint32_t)(thread_rel - warp_rel);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (cnt[j]) {
+        const Span r = decode_span(sp[j]);
+        const uint32_t slot = (uint32_t)(lane * kScanItems + j);
+        const uint32_t origin = r.y0 * (uint32_t)tiles_x + r.x0;
+        if (r.area <= (uint32_t)kCullMaxTiles) {
+          unsigned long long m = r.mask;
+          const uint32_t inv = (65536u + r.w - 1u) / r.w;  // exact row = bit / w for bit < 64
+          while (m) {
+            const uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
+            m &= m - 1;
+            const uint32_t row = (bit * inv) >> 16, col = bit - row * r.w;
+            stage[off++] = ((origin + row * (uint32_t)tiles_x + col) << 7) | slot;
+          }
+        } else {
+          for (uint32_t ty = 0; ty < r.h; ++ty)
+            for (uint32_t tx = 0; tx < r.w; ++tx) stage[off++] = ((origin + ty * (uint32_t)tiles_x + tx) << 7) | slot;
+        }
+      }
+    }
+  } else if (warp_total != 0) {
+    unsigned long long run = thread_rel - warp_rel;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      s_off[lane * kScanItems + j] = (uint32_t)(run < 0xFFFFFFFFull ? run : 0xFFFFFFFFull);
+      run += cnt[j];
+    }
+  }
   if (warp == 0) {
     unsigned long long prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u64(status, kScanInclusive | total);
-    } else {
-      if (lane == 0) st_volatile_u64(status + tile, kScanAggregate | total);
+    if (tile != 0) {
       int64_t win = (int64_t)tile - 1;  // newest predecessor of the current window
       while (true) {
         const int64_t mine_idx = win - lane;
@@ -180,50 +233,9 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
       }
     }
   }
-  __syncthreads();
-  // ---- emission.  The 128 Gaussians of a warp own one contiguous output range.  Every lane expands ITS Gaussians
-  //      (a walk over the set bits of the keep mask: a few instructions per pair) into the warp's staging buffer in
-  //      shared memory, at the offset its prefix gives; the warp then copies the buffer out with coalesced 128-byte
-  //      stores.  A staged pair is one word, tile << 7 | slot of the Gaussian in the warp.  (A first version let
-  //      every lane binary-search the owner of each output element: ~170 thread instructions per pair.)  Warps whose
-  //      range exceeds the buffer - a few huge splats - fall back to that search, element by element.
-  uint32_t *stage = s_dyn + (size_t)warp * kStageWords;
-  uint32_t *s_gid = stage + kStageCap;
-  uint32_t *s_off = s_gid + 32 * kScanItems;
-  const unsigned long long thread_excl = s_base + pre + inc - mine;  // pairs before this thread's first Gaussian
-  const unsigned long long warp_out = __shfl_sync(0xFFFFFFFFu, thread_excl, 0);
-  const unsigned long long warp_total = __shfl_sync(0xFFFFFFFFu, thread_excl + mine, 31) - warp_out;
-  if (blend_rank) {  // every entry of the compacted order is blended: its rank is its position
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j)
-      if (gid[j] != 0xFFFFFFFFu) blend_rank[gid[j]] = (uint32_t)(first + j);
-  }
-#pragma unroll
-  for (int j = 0; j < kScanItems; ++j) s_gid[lane * kScanItems + j] = gid[j];
-  if (warp_total != 0 && warp_total <= (unsigned long long)kStageCap) {
-    uint32_t off = (uint32_t)(thread_excl - warp_out);
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-      if (cnt[j]) {
-        const Span r = decode_span(sp[j]);
-        const uint32_t slot = (uint32_t)(lane * kScanItems + j);
-        const uint32_t origin = r.y0 * (uint32_t)tiles_x + r.x0;
-        if (r.area <= (uint32_t)kCullMaxTiles) {
-          unsigned long long m = r.mask;
-          const uint32_t inv = (65536u + r.w - 1u) / r.w;  // exact row = bit / w for bit < 64
-          while (m) {
-            const uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
-            m &= m - 1;
-            const uint32_t row = (bit * inv) >> 16, col = bit - row * r.w;
-            stage[off++] = ((origin + row * (uint32_t)tiles_x + col) << 7) | slot;
-          }
-        } else {
-          for (uint32_t ty = 0; ty < r.h; ++ty)
-            for (uint32_t tx = 0; tx < r.w; ++tx) stage[off++] = ((origin + ty * (uint32_t)tiles_x + tx) << 7) | slot;
-        }
-      }
-    }
-    __syncwarp();
+  __syncthreads();  // s_base is known; every warp's staging buffer (written by its own lanes) is complete
+  const unsigned long long warp_out = s_base + warp_rel;
+  if (staged) {
     for (uint32_t e = lane; e < (uint32_t)warp_total; e += 32) {
       const unsigned long long out = warp_out + e;
       if (out < capacity) {
@@ -236,15 +248,6 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
     }
   } else if (warp_total != 0) {
     // ---- fallback for a warp with more pairs than the staging buffer holds ----
-    {
-      unsigned long long run = thread_excl - warp_out;
-#pragma unroll
-      for (int j = 0; j < kScanItems; ++j) {
-        s_off[lane * kScanItems + j] = (uint32_t)(run < 0xFFFFFFFFull ? run : 0xFFFFFFFFull);
-        run += cnt[j];
-      }
-    }
-    __syncwarp();
     const unsigned long long room = capacity > warp_out ? capacity - warp_out : 0ull;  // pairs beyond it are dropped
     const uint32_t limit = (uint32_t)(warp_total < room ? warp_total : room);          // <= capacity < 2^30
     for (uint32_t e = lane; e < limit; e += 32) {
