@@ -88,8 +88,9 @@ int gsr_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
  * denominator of the blend stage's roofline.  Synchronises; diagnostics only. */
 int gsr_fp32_fma_peak(double *tflops, double *sm_mhz_effective);
 /* Diagnostics: choose the blend kernel's staging path (0 = cp.async per CTA, 1 = cp.async.bulk + mbarrier, 2 = cp.async
- * per warp) and the batched rejection test (0 / 1) at run time; stage < 0 returns to the built-in default (or the
- * GSR_BLEND_STAGE / GSR_BLEND_PRETEST environment variables).  All variants produce bit-identical images. */
+ * per warp, the default) at run time; stage < 0 returns to the built-in default (or the GSR_BLEND_STAGE environment
+ * variable).  `pretest` is ignored (a variant that was measured and removed).  All variants produce bit-identical
+ * images. */
 int gsr_debug_blend_variant(int stage, int pretest);
 
 /* ---------------------------------------------------------------------------------------------

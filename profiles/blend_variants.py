@@ -18,8 +18,7 @@ import torch
 from gsr_b200 import _cabi, camera, render as R, scenes
 
 NAMES = {0: "cp.async per CTA (128-record batches, 2 barriers per batch)", 1: "cp.async.bulk + mbarrier (TMA unit)",
-         2: "cp.async per warp (64-record batches, no CTA barrier)",
-         3: "cp.async per warp, one 32-thread CTA per half tile"}
+         2: "cp.async per warp (64-record batches, no CTA barrier)"}
 
 
 def main(config="C3"):
@@ -32,7 +31,7 @@ def main(config="C3"):
     torch.cuda.synchronize()
     out, ref_img = [], None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for stage, pre in ((0, 0), (2, 0), (3, 0), (1, 0), (0, 0), (2, 0), (3, 0)):
+    for stage, pre in ((0, 0), (2, 0), (1, 0), (0, 0), (2, 0)):
         _cabi.call("gsr_debug_blend_variant", stage, pre)
         for _ in range(5):
             st.blend()

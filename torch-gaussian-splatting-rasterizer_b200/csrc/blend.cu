@@ -47,19 +47,18 @@ constexpr float kParkedY = 1e18f;
 // (A fourth variant - the rejection tests of a group of four records evaluated back to back before any of the four is
 // blended, for instruction-level parallelism - needed 80 registers and measured 0.47-0.48 ms against 0.40-0.42; it was
 // removed after the measurement, profiles/r02_blend_variants_C3.json.)
-//   kStageHalf  kStageWarp with one CTA per WARP (32 threads, two CTAs per tile): a warp that has finished its half tile
-//               frees its slot at once instead of waiting for the tile's other warp.
-constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2, kStageHalf = 3;
+// (Also measured and removed: kStageWarp with one 32-thread CTA per half tile, so that a finished warp frees its slot at
+// once - 0.405 ms against 0.404, no gain; profiles/r02_blend_variants_C3_final.json.)
+constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2;
 
 template <int PX, bool COUNT, bool RANKED, bool TRACK, int STAGE>
-__global__ void __launch_bounds__(STAGE == kStageHalf ? 32 : 256 / PX,
-                                  (PX == 4 && !GSR_BAND_INLINE) ? (STAGE == kStageHalf ? 32 : 18) : 1)  // <= 56 / 64 registers
+__global__ void __launch_bounds__(256 / PX, (PX == 4 && !GSR_BAND_INLINE) ? 18 : 1)  // 18 CTAs/SM: <= 56 registers
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
              uint32_t *__restrict__ n_contrib, gsr_frame_info *info, float neg_zero) {
-  constexpr bool BULK = STAGE == kStageBulk, HALF = STAGE == kStageHalf, SOLO = STAGE == kStageWarp || HALF;
-  constexpr int THREADS = HALF ? 32 : 256 / PX;
+  constexpr bool BULK = STAGE == kStageBulk, SOLO = STAGE == kStageWarp;
+  constexpr int THREADS = 256 / PX;
   constexpr int WARPS = THREADS / 32;
   constexpr int kBatch = SOLO ? 64 : (PX >= 8 ? 64 : 128);  // records per staged batch
   constexpr int GATHERERS = SOLO ? 32 : THREADS;            // threads that share the gather of one batch
@@ -69,13 +68,13 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x;
-  const int tile_x = HALF ? blockIdx.x >> 1 : blockIdx.x, tile_y = blockIdx.y + row_begin;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y + row_begin;
   // Lane -> pixel map: a warp owns 8 columns x 16 rows of the tile... a thread owns ONE column (dx is shared by its PX
   // pixels) and the rows r, r+R, r+2R, ... with R = 16/PX, so that pixel slot k of the warp is the compact 8 x R block
   // of rows kR..kR+R-1: a Gaussian reaches few slots, and a slot whose 32 pixels all fail the test costs nothing.
   constexpr int R = GSR_TILE / PX;            // rows per slot block
   constexpr int COLS = 32 / R;                // columns per warp
-  const int lane = tid & 31, warp = HALF ? (blockIdx.x & 1) : tid >> 5;  // `warp` = which half of the tile
+  const int lane = tid & 31, warp = tid >> 5;
   const int gtid = SOLO ? lane : tid;         // index among the threads that gather a batch together
   const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
   const int py0 = tile_y * GSR_TILE + (lane / COLS);
@@ -114,7 +113,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
     }
     __syncthreads();
   }
-  float *const my_bufs = (SOLO && !HALF) ? &s_rec[2 * warp][0] : &s_rec[0][0];  // this thread's double buffer
+  float *const my_bufs = SOLO ? &s_rec[2 * warp][0] : &s_rec[0][0];  // this thread's double buffer
   uint32_t gnext[PER];
   auto load_ids = [&](int b) {
 #pragma unroll
@@ -330,14 +329,14 @@ static int blend_variant() {
   static const int from_env = [] {
     const char *e = getenv("GSR_BLEND_STAGE");
     int stage = GSR_DEFAULT_BLEND_STAGE;
-    if (e) stage = e[0] == 'b' ? kStageBulk : (e[0] == 'w' ? kStageWarp : (e[0] == 'h' ? kStageHalf : kStageCta));
+    if (e) stage = e[0] == 'b' ? kStageBulk : (e[0] == 'w' ? kStageWarp : kStageCta);
     return stage;
   }();
   return g_blend_variant >= 0 ? g_blend_variant : from_env;
 }
 extern "C" int gsr_debug_blend_variant(int stage, int pretest) {
   (void)pretest;  // the batched rejection test was measured and removed (kept in the signature for ABI stability)
-  g_blend_variant = (stage < 0) ? -1 : (stage & 3);
+  g_blend_variant = (stage < 0) ? -1 : (stage % 3);
   return GSR_OK;
 }
 
@@ -367,8 +366,7 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
   const int variant = blend_variant();
   const int stage_sel = variant & 3;
 #define GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, STAGE)                                                          \
-  blend_kernel<PX, COUNT, RANKED, TRACK, STAGE><<<(STAGE == kStageHalf ? dim3(grid.x * 2, grid.y) : grid),             \
-                                                  (STAGE == kStageHalf ? 32 : 256 / PX), 0, (cudaStream_t)stream>>>(   \
+  blend_kernel<PX, COUNT, RANKED, TRACK, STAGE><<<grid, 256 / PX, 0, (cudaStream_t)stream>>>(                        \
       (const float4 *)rec, tile_gids, (const uint2 *)tile_ranges, width, height, tg.tiles_x, tile_row_begin,       \
       blend_rank, first_rank, last_rank, image, final_T, n_contrib, info_dev, -0.0f)
 #define GSR_BLEND_LAUNCH(PX, COUNT, RANKED, TRACK)                                                                 \
@@ -376,7 +374,6 @@ extern "C" int gsr_blend_fwd(const float *rec, const uint32_t *tile_gids, const 
     if (PX != 4) GSR_BLEND_LAUNCH1(PX, COUNT, RANKED, TRACK, kStageCta);                                            \
     else if (stage_sel == kStageBulk) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageBulk);                       \
     else if (stage_sel == kStageWarp) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageWarp);                       \
-    else if (stage_sel == kStageHalf) GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageHalf);                       \
     else GSR_BLEND_LAUNCH1(4, COUNT, RANKED, TRACK, kStageCta);                                                     \
   } while (0)
 #define GSR_BLEND_PICK2(PX, COUNT, RANKED)                                                                         \
