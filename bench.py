@@ -33,6 +33,9 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL prints its version banner to STDOUT at this level; the
+    os.environ["NCCL_DEBUG"] = "WARN"                         # contract is ONE JSON line there
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
