@@ -375,8 +375,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the Gaussian count (debugging only)")
     ap.add_argument("--orbit", action="store_true", help="N=1 only: render the 256-view orbit of the N>1 workload (to separate view cost from scaling loss)")
-    ap.add_argument("--gather", choices=["none", "nccl", "p2p", "p2p-rr"], default="p2p",
-                    help="N>1: how finished frames are gathered in the timed loop (all modes are also reported in gather_modes)")
+    ap.add_argument("--gather", choices=["none", "nccl", "p2p", "p2p-rr"], default="p2p-rr",
+                    help="N>1: how finished frames are gathered in the timed loop (every mode is also measured and reported in "
+                         "gather_modes).  Default: each step's N frames go to ONE consumer rank, round-robin, by peer DMA - "
+                         "what a consumer of frames (an encoder per rank) needs, 1/N of an all-gather's traffic; measured at "
+                         "N=8 (profiles/r02_bench_8gpu_allgather.json): no gather 9976 fps, this 9886, peer-DMA all-gather "
+                         "9233, NCCL all_gather 8322 - the scaling loss of round 1 was the all-gather's HBM/NVLink traffic")
     ap.add_argument("--graph", action="store_true", help="replay each frame from a captured CUDA graph")
     ap.add_argument("--ring", type=int, default=8, help="frame buffers per rank (N>1): how far a rank may run ahead of the gather")
     ap.add_argument("--cpu-budget", type=float, default=20.0)

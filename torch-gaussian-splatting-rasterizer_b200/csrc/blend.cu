@@ -162,6 +162,24 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       if (T[k] < kStopT) fy[k] = kParkedY;     // stop AFTER the blend that crosses 1e-4
     }
   };
+  // The same, for a record whose four powers are all <= 0 and whose opacity is below 0.9899 - nearly every record: the
+  // `power <= 0` half of the keep test (:291) is then true for every pixel, and min(alpha, 0.99) is the identity
+  // (ex2.approx(power log2e + log2 o) <= o (1 + 1e-5) < 0.99), so both drop out of the per-pixel code.  Same alpha, same
+  // decision, bit for bit; anything near the 1/255 threshold still goes through the exact band path.
+  auto blend_slot_plain = [&](int k, float power, float opacity, float log2o, float cr, float cg, float cb, uint32_t pos) {
+    float alpha = ex2_approx(fmaf(power, 1.4426950408889634f, log2o));
+    bool keep = alpha > kBandHi;
+    if (!keep) keep = blend_alpha_band(power, opacity, alpha);
+    if (keep) {
+      const float wgt = alpha * T[k];
+      C0[k] = fmaf(wgt, cr, C0[k]);
+      C1[k] = fmaf(wgt, cg, C1[k]);
+      C2[k] = fmaf(wgt, cb, C2[k]);
+      T[k] = fmaf(-alpha, T[k], T[k]);
+      if (TRACK) last[k] = pos;
+      if (T[k] < kStopT) fy[k] = kParkedY;
+    }
+  };
   auto powers = [&](const float *r, float power[PX], float &thr) -> bool {
     const float4 q = *reinterpret_cast<const float4 *>(r);      // mx my A C
     const float2 w = *reinterpret_cast<const float2 *>(r + 4);  // B thr
@@ -210,9 +228,18 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
         if (powers(r, power, thr)) {
           const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
           const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
+          float pmax = power[0];
 #pragma unroll
-          for (int k = 0; k < PX; ++k)
-            if (power[k] >= thr) blend_slot(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
+          for (int k = 1; k < PX; ++k) pmax = fmaxf(pmax, power[k]);
+          if (pmax <= 0.0f && orr.x < 0.9899f) {
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+              if (power[k] >= thr) blend_slot_plain(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
+          } else {
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+              if (power[k] >= thr) blend_slot(k, power[k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
+          }
         }
       }
       // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where

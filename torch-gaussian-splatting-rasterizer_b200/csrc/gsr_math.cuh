@@ -233,11 +233,18 @@ __device__ __forceinline__ bool tile_is_empty(const CullGaussian &g, float px0, 
     const float cu = fminf(fmaxf(0.0f, u0), u1), cv = fminf(fmaxf(0.0f, v0), v1);
     if (fmaf(g.A * cu, cu, fmaf(g.C * cv, cv, g.B * cu * cv)) >= g.limit) return false;
   }
-  // edges u = u0 / u1: f(v) = C v^2 + (B u) v + A u^2 ; edges v = v0 / v1: f(u) = A u^2 + (B v) u + C v^2
-  float best = parabola_max(g.C, g.B * u0, g.A * u0 * u0, g.kv * u0, v0, v1);
-  best = fmaxf(best, parabola_max(g.C, g.B * u1, g.A * u1 * u1, g.kv * u1, v0, v1));
-  best = fmaxf(best, parabola_max(g.A, g.B * v0, g.C * v0 * v0, g.ku * v0, u0, u1));
-  best = fmaxf(best, parabola_max(g.A, g.B * v1, g.C * v1 * v1, g.ku * v1, u0, u1));
+  // Only the edges that FACE the mean can hold the maximum.  At the maximiser p* of a concave f over the box the gradient
+  // lies in the normal cone of the box; for a negative definite quadratic grad f(p) . p = 2 f(p) < 0, so an outward normal
+  // (+1, 0) at p* needs u1 < 0, (-1, 0) needs u0 > 0, likewise in v: the edge u = u0 qualifies only when the box lies to
+  // the right of the mean, u = u1 only when it lies to the left (a corner maximiser belongs to a qualifying edge too).
+  // At most one vertical and one horizontal edge qualify (the mean is not inside): two clamped parabolas instead of four.
+  // edge u = eu: f(v) = C v^2 + (B eu) v + A eu^2 ; edge v = ev: f(u) = A u^2 + (B ev) u + C ev^2
+  const float eu = u0 > 0.0f ? u0 : u1, ev = v0 > 0.0f ? v0 : v1;
+  const float fu = parabola_max(g.C, g.B * eu, g.A * eu * eu, g.kv * eu, v0, v1);
+  const float fv = parabola_max(g.A, g.B * ev, g.C * ev * ev, g.ku * ev, u0, u1);
+  const float ninf = __int_as_float(0xff800000);
+  float best = fmaxf((u0 > 0.0f || u1 < 0.0f) ? fu : ninf, (v0 > 0.0f || v1 < 0.0f) ? fv : ninf);
+  if (!(fu == fu) || !(fv == fv)) best = __int_as_float(0x7fc00000);  // any NaN: keep the tile (the comparison below is false)
   // rounding margin proportional to the largest term that can cancel inside `power` on this box
   const float U = fmaxf(fabsf(u0), fabsf(u1)), V = fmaxf(fabsf(v0), fabsf(v1));
   const float mag = fabsf(g.A) * U * U + fabsf(g.C) * V * V + fabsf(g.B) * U * V;

@@ -8,6 +8,9 @@
 namespace gsr {
 
 constexpr int kPreThreads = 256;
+#ifndef GSR_PRE_CTAS
+#define GSR_PRE_CTAS 3   // resident CTAs per SM the prepared kernel is compiled for (79 registers; 4 would need <= 64)
+#endif
 
 // ---- the per-Gaussian body shared by the two preprocess kernels ------------------------------------------------
 // preprocess_kernel         reads the RAW strided parameters (any torch view) and computes everything per view;
@@ -339,7 +342,7 @@ prepare_kernel(const gsr_gaussians g, float4 *__restrict__ geom, float4 *__restr
 
 // Per-view kernel over the prepared model: one warp per block of 32 Gaussians, persistent.
 template <int DEGREE>
-__global__ void __launch_bounds__(kPreThreads, 3)
+__global__ void __launch_bounds__(kPreThreads, GSR_PRE_CTAS)
 preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__restrict__ shb, int64_t n,
                            const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
                            uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
