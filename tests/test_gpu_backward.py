@@ -141,10 +141,12 @@ def test_band_gradients_sum_to_the_full_gradient():
 def test_finite_difference_spot_checks_at_scale():
     """Large-scale backward validation: at 300 k Gaussians autograd through a per-Gaussian CPU loop is out of
     reach, so a random subset of Gaussians is checked by central finite differences of the (parity-checked) CUDA forward:
-    position, log-scale, opacity logit and an SH coefficient, loss = sum(image * G) with G random inside a window around
-    the splat.  The forward is only piecewise smooth (the keep test alpha > 1/255 moves with the parameters and carries
-    no gradient, as in autograd), so individual entries may be off by the rim's contribution: the bar is on the
-    distribution - median relative error < 3 %, 80 % of the entries within 10 %."""
+    position, log-scale, opacity logit and an SH coefficient, loss = sum(image * G) with G a smooth ramp inside a window
+    around the splat (so that every parameter's gradient is a coherent sum over the footprint) and the splats taken from
+    the front fifth of the depth order (high transmittance).  The forward is only piecewise smooth - the keep test
+    alpha > 1/255 moves with the parameters and carries no gradient, as in autograd; its rim contributes about
+    1/(255 o) of an opacity or scale derivative - so the bar is on the distribution: median relative error < 3 %, 80 % of
+    the entries within 10 %."""
     import json
     import os
 
@@ -160,11 +162,14 @@ def test_finite_difference_spot_checks_at_scale():
     pre = R.preprocess(model, cam)
     tt = (pre["tiles_touched"] & 0x7FFFFFFF).cpu().numpy()
     rec = pre["rec"].cpu().numpy()
-    ok = (tt >= 2) & (tt <= 12) & (rec[:, 6] > 0.35) & (rec[:, 0] > 40) & (rec[:, 0] < W - 40) & (rec[:, 1] > 40) & (rec[:, 1] < H - 40)
+    key = pre["depth_key"].cpu().numpy().view(np.uint32)
+    vis = tt > 0
+    front = key <= np.quantile(key[vis], 0.2)
+    ok = vis & front & (tt >= 2) & (tt <= 12) & (rec[:, 6] > 0.35) & (rec[:, 0] > 40) & (rec[:, 0] < W - 40) & (rec[:, 1] > 40) & (rec[:, 1] < H - 40)
     cand = np.nonzero(ok)[0]
-    assert cand.shape[0] > 1000
+    assert cand.shape[0] > 500
     rng = np.random.default_rng(3)
-    picks = rng.choice(cand, 12, replace=False)
+    picks = rng.choice(cand, 16, replace=False)
     r = R.Renderer()
     rel_errs, rows = [], []
     for g in picks.tolist():
@@ -173,7 +178,10 @@ def test_finite_difference_spot_checks_at_scale():
         x0, x1 = max(int(mx) - half, 0), min(int(mx) + half + 1, W)
         y0, y1 = max(int(my) - half, 0), min(int(my) + half + 1, H)
         G = torch.zeros((H, W, 3), device="cuda")
-        G[y0:y1, x0:x1] = torch.from_numpy(rng.uniform(-1, 1, (y1 - y0, x1 - x0, 3)).astype(np.float32)).cuda()
+        yy, xx = np.meshgrid(np.arange(y0, y1), np.arange(x0, x1), indexing="ij")
+        a, b = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+        ramp = 1.0 + ((xx - mx) / half)[..., None] * a + ((yy - my) / half)[..., None] * b   # smooth, per-channel slopes
+        G[y0:y1, x0:x1] = torch.from_numpy(ramp.astype(np.float32)).cuda()
         leaves = [t.clone().requires_grad_(True) for t in (model.xyz, model.log_scales, model.rots, model.opacity, model.sh)]
         (R.render_differentiable(*leaves, cam, renderer=r) * G).sum().backward()
         grads = [t.grad for t in leaves]
@@ -192,7 +200,7 @@ def test_finite_difference_spot_checks_at_scale():
             tensor[idx] = old
             fd, an = (lp - lm) / (2 * h), float(grad)
             scale = max(abs(fd), abs(an))
-            if scale < 1e-3:  # nothing to compare (colour clamped, pixels saturated)
+            if scale < 1e-2:  # nothing to compare (colour clamped, splat hidden)
                 continue
             rel = abs(fd - an) / scale
             rel_errs.append(rel)
