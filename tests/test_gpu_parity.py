@@ -336,7 +336,8 @@ def test_prepared_preprocess_is_bit_identical(name, R):
     tt = a["tiles_touched"]
     assert torch.equal(a["depth_key"], b["depth_key"])
     assert torch.equal(tt, b["tiles_touched"])
-    assert torch.equal(a["tile_span"], b["tile_span"])
+    blendable = (tt >> 31) != 0                         # spans are only ever read for Gaussians the loop blends (a
+    assert torch.equal(a["tile_span"][blendable], b["tile_span"][blendable])  # block that is off screen as a whole skips them)
     assert torch.equal(a["depth_hist"], b["depth_hist"])
     vis = (tt & 0x7FFFFFFF) != 0                       # records are written for Gaussians that keep a tile
     assert torch.equal(a["rec"][vis].view(torch.int32), b["rec"][vis].view(torch.int32))
@@ -344,7 +345,8 @@ def test_prepared_preprocess_is_bit_identical(name, R):
     # band mode goes through the same body
     rows = (1, 3)
     a2, b2 = R.preprocess(model, cam, tile_rows=rows), R.preprocess(model, cam, tile_rows=rows, prepared=True)
-    assert torch.equal(a2["tile_span"], b2["tile_span"]) and torch.equal(a2["tiles_touched"], b2["tiles_touched"])
+    bl2 = (a2["tiles_touched"] >> 31) != 0
+    assert torch.equal(a2["tile_span"][bl2], b2["tile_span"][bl2]) and torch.equal(a2["tiles_touched"], b2["tiles_touched"])
     # whole frames: bit-identical images, and the strided (interleaved SH) input prepares to the same model
     r = R.Renderer()
     img_p, img_r = r.render(model, cam, prepared=True).clone(), r.render(model, cam, prepared=False)
