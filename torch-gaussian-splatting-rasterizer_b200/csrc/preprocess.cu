@@ -356,23 +356,6 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
   const TileGrid tg = make_grid(cam.width, cam.height);
   const PreDebug dbg = {nullptr, nullptr, nullptr, nullptr};
   const int64_t blocks = (n + 31) >> 5;
-  // Whole-warp early out.  A block of 32 Gaussians none of which can reach the screen (or this rank's band) skips the
-  // EWA projection, the culling and the SH rows altogether - which pays when neighbours in memory are neighbours in
-  // space (a spatially ordered prepared model), because then most off-screen Gaussians sit in all-off-screen blocks.
-  // The test is conservative: lambda_max(cov2d) <= |J|_F^2 |W|_F^2 tr(Sigma) + 0.3 and the reference's
-  // radius = ceil(3 sqrt(lambda_1)), lambda_1 <= tr(cov2d) + sqrt(0.1) (rasterize.py:171-181), with
-  // |J|_F^2 <= (fx^2 (1 + limx^2) + fy^2 (1 + limy^2)) / z^2 (:218-228: |t_x / z| is clamped to limx); a Gaussian whose
-  // bound misses the pixel rect by more than a tile has an empty tile rect in the full computation, i.e. is not
-  // blendable and writes exactly what is written here (depth key; no tiles).
-  float w2 = 0.0f;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) w2 = fmaf(cam.w2c_t[a * 4 + b], cam.w2c_t[a * 4 + b], w2);
-  const float jw2 = w2 * (cam.focal_x * cam.focal_x * (1.0f + cam.limx * cam.limx) +
-                          cam.focal_y * cam.focal_y * (1.0f + cam.limy * cam.limy));
-  const float y_lo = (float)(max(row_begin, 0) * GSR_TILE) - 16.0f;
-  const float y_hi = (float)min((long long)cam.height, (long long)min(row_end, 1 << 24) * GSR_TILE) + 16.0f;
   for (int64_t blk = (int64_t)blockIdx.x * (kPreThreads / 32) + warp; blk < blocks; blk += (int64_t)gridDim.x * (kPreThreads / 32)) {
     const int64_t i = blk * 32 + lane;
     const bool active = i < n;
@@ -380,27 +363,6 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
     const float4 q0 = __ldg(gp), q1 = __ldg(gp + 32), q2 = __ldg(gp + 64);
     const float p[3] = {q0.x, q0.y, q0.z};
     const float S6[6] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-    {
-      const float cz = row_affine(cam.w2c_t, 2, p[0], p[1], p[2]);  // the depth pre_body computes (same expression)
-      bool maybe = active && !(cz < 0.2f);
-      if (maybe) {
-        const float pw = frcp(fadd(row_affine(cam.full_t, 3, p[0], p[1], p[2]), 0.0000001f));
-        const float mx = fmul(fsub(fmul(fadd(fmul(row_affine(cam.full_t, 0, p[0], p[1], p[2]), pw), 1.0f), (float)cam.width), 1.0f), 0.5f);
-        const float my = fmul(fsub(fmul(fadd(fmul(row_affine(cam.full_t, 1, p[0], p[1], p[2]), pw), 1.0f), (float)cam.height), 1.0f), 0.5f);
-        const float tr = (S6[0] + S6[3]) + S6[5];
-        const float rb = 3.003f * sqrtf(jw2 * tr / (cz * cz) + 0.92f) + 2.0f;
-        const bool off = (mx + rb < -16.0f) || (mx - rb > (float)cam.width + 16.0f) || (my + rb < y_lo) || (my - rb > y_hi);
-        maybe = !off;  // NaN / inf anywhere: every comparison is false, the Gaussian takes the full path
-      }
-      if (!__any_sync(0xFFFFFFFFu, maybe)) {
-        if (active) {
-          depth_key[i] = float_to_key(cz);
-          tiles_touched[i] = 0u;
-          span_out[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        continue;
-      }
-    }
     const float4 *sp = shb + blk * (kPrepShRows * 32) + lane;
     auto colour = [&](float dx, float dy, float dz, float rgb[3]) {
       float4 v[3][rows];
