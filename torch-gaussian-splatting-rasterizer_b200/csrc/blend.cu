@@ -25,6 +25,9 @@
 
 #include "blend_common.cuh"
 
+#ifndef GSR_BLEND_GROUP
+#define GSR_BLEND_GROUP 4   // records walked per warp vote (unrolled); 2 halves the loop body (A/B builds)
+#endif
 #ifndef GSR_DEFAULT_BLEND_STAGE
 #define GSR_DEFAULT_BLEND_STAGE 2   // kStageWarp: measured fastest (profiles/r02_blend_variants_C3.json)
 #endif
@@ -210,11 +213,11 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   auto eval_batch = [&](const float *base, int count, uint32_t list_base) {
     // The list is walked four records at a time with no bound check inside the group: slots past the end of the
     // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
-    const int count4 = (count + 3) & ~3;
-    for (int j = 0; j < count4; j += 4) {
+    const int count4 = (count + (GSR_BLEND_GROUP - 1)) & ~(GSR_BLEND_GROUP - 1);
+    for (int j = 0; j < count4; j += GSR_BLEND_GROUP) {
       if (COUNT) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < GSR_BLEND_GROUP; ++u)
           if (j + u < count) {
             ++my_iters;
 #pragma unroll
@@ -222,7 +225,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GSR_BLEND_GROUP; ++u) {
         const float *r = base + (j + u) * GSR_REC_FLOATS;
         float power[PX], thr;
         if (powers(r, power, thr)) {

@@ -3,11 +3,16 @@
 // warp reads one full 128-byte line (HBM-bound stage: 236 B in / 64 B out per Gaussian at SH degree 3).
 //
 // Replaces /root/reference/rasterize.py:97-120, 358, 371-420, 441 and spherical_harmonics.py:27-73.
+#include <stdlib.h>
+
 #include "gsr_math.cuh"
 
 namespace gsr {
 
 constexpr int kPreThreads = 256;
+#ifndef GSR_PRE_PREFETCH
+#define GSR_PRE_PREFETCH 1   // L2 prefetch of the block's SH rows and the next block's geometry: 0.185 -> 0.169 ms (r02_notes)
+#endif
 #ifndef GSR_PRE_CTAS
 #define GSR_PRE_CTAS 3   // resident CTAs per SM the prepared kernel is compiled for (79 registers; 4 would need <= 64)
 #endif
@@ -356,11 +361,52 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
   const TileGrid tg = make_grid(cam.width, cam.height);
   const PreDebug dbg = {nullptr, nullptr, nullptr, nullptr};
   const int64_t blocks = (n + 31) >> 5;
+#if GSR_PRE_PREFETCH == 2
+  float4 nq0 = make_float4(0.f, 0.f, 0.f, 0.f), nq1 = nq0, nq2 = nq0;
+  {
+    const int64_t b0 = (int64_t)blockIdx.x * (kPreThreads / 32) + warp;
+    if (b0 < blocks) {
+      const float4 *g0 = geom + b0 * (kPrepGeomRows * 32) + lane;
+      nq0 = __ldg(g0); nq1 = __ldg(g0 + 32); nq2 = __ldg(g0 + 64);
+    }
+  }
+#endif
   for (int64_t blk = (int64_t)blockIdx.x * (kPreThreads / 32) + warp; blk < blocks; blk += (int64_t)gridDim.x * (kPreThreads / 32)) {
     const int64_t i = blk * 32 + lane;
     const bool active = i < n;
     const float4 *gp = geom + blk * (kPrepGeomRows * 32) + lane;
+#if GSR_PRE_PREFETCH == 2
+    const float4 q0 = nq0, q1 = nq1, q2 = nq2;  // loaded during the previous iteration
+    {
+      const int64_t nb = blk + (int64_t)gridDim.x * (kPreThreads / 32);
+      if (nb < blocks) {
+        const float4 *gn = geom + nb * (kPrepGeomRows * 32) + lane;
+        nq0 = __ldg(gn); nq1 = __ldg(gn + 32); nq2 = __ldg(gn + 64);
+      }
+    }
+#else
     const float4 q0 = __ldg(gp), q1 = __ldg(gp + 32), q2 = __ldg(gp + 64);
+#endif
+#if GSR_PRE_PREFETCH
+    {  // L2 prefetch: this block's SH rows (wanted ~400 instructions from now, and fetched from DRAM at sector granularity
+       // whether or not the neighbours turn out visible) and the next block's geometry rows - no registers held
+      const float4 *spf = shb + blk * (kPrepShRows * 32) + lane;
+#pragma unroll
+      for (int r = 0; r < 3 * rows; ++r) {
+        const int c = r / rows, j = r % rows;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(spf + (c * 4 + j) * 32));
+      }
+#if GSR_PRE_PREFETCH == 1
+      const int64_t nb = blk + (int64_t)gridDim.x * (kPreThreads / 32);
+      if (nb < blocks) {
+        const float4 *gn = geom + nb * (kPrepGeomRows * 32) + lane;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + 64));
+      }
+#endif
+    }
+#endif
     const float p[3] = {q0.x, q0.y, q0.z};
     const float S6[6] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
     const float4 *sp = shb + blk * (kPrepShRows * 32) + lane;
@@ -473,7 +519,13 @@ int launch_preprocess_prepared(const void *prepared, int64_t n, const gsr_camera
   const float4 *geom = (const float4 *)prepared;
   const float4 *shb = (const float4 *)((const char *)prepared + prepared_geom_bytes(n));
   unsigned blocks = blocks_for(prepared_blocks(n), kPreThreads / 32);
-  const unsigned resident = (unsigned)sm_count() * 6;  // persistent: a few CTAs per SM, each loops over its share
+  // persistent: GSR_PRE_GRID CTAs per SM (default 6 = two rounds of the 3 that are resident), each loops over its share
+  static const int per_sm = [] {
+    const char *e = getenv("GSR_PRE_GRID");
+    const int v = e ? atoi(e) : 6;
+    return (v < 1 || v > 64) ? 6 : v;
+  }();
+  const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
   if (blocks > resident) blocks = resident;
 #define GSR_PRE(D)                                                                                                  \
   preprocess_prepared_kernel<D><<<blocks, kPreThreads, 0, stream>>>(geom, shb, n, *cam, row_begin, row_end, depth_key, \
