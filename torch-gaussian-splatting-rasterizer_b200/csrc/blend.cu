@@ -25,6 +25,12 @@
 
 #include "blend_common.cuh"
 
+#ifndef GSR_BLEND_WBATCH
+#define GSR_BLEND_WBATCH 32   // records per per-warp staging batch (kStageWarp): 32 -> 0.391 ms, 64 -> 0.399 (r02_notes)
+#endif
+#ifndef GSR_BLEND_MINCTAS
+#define GSR_BLEND_MINCTAS 18  // resident CTAs per SM the 4-pixel kernel is compiled for (18: <= 56 registers)
+#endif
 #ifndef GSR_BLEND_GROUP
 #define GSR_BLEND_GROUP 4   // records walked per warp vote (unrolled); 2 halves the loop body (A/B builds)
 #endif
@@ -41,9 +47,9 @@ constexpr float kParkedY = 1e18f;
 //               three 16-byte asynchronous copies; completion by cp.async.wait_group + the batch barrier;
 //   kStageBulk  cp.async.bulk (the TMA unit, SASS UBLKCP): one 48-byte bulk copy per record, completion counted in
 //               bytes by an mbarrier (expect_tx / complete_tx) that the consumers wait on - no wait_group;
-//   kStageWarp  cp.async, one double buffer per WARP (64-record batches): the two warps of a tile never meet at a
+//   kStageWarp  cp.async, one double buffer per WARP (32-record batches): the two warps of a tile never meet at a
 //               barrier - each gathers the list for itself (the second read of a record hits L2), walks it at its own
-//               pace and leaves when its 128 pixels are done.
+//               pace and leaves when its 128 pixels are done.  (32-record batches: one record per lane and batch.)
 // All deliver the same bytes in the same order; the image is bit-identical (tests/test_gpu_edges.py).  Which one is the
 // default is a measurement (profiles/r02_notes.md): the lists are GATHERS of scattered 48-byte records, so the bulk path
 // needs one TMA operation per record, issued from uniform registers one lane at a time.
@@ -55,7 +61,7 @@ constexpr float kParkedY = 1e18f;
 constexpr int kStageCta = 0, kStageBulk = 1, kStageWarp = 2;
 
 template <int PX, bool COUNT, bool RANKED, bool TRACK, int STAGE>
-__global__ void __launch_bounds__(256 / PX, (PX == 4 && !GSR_BAND_INLINE) ? 18 : 1)  // 18 CTAs/SM: <= 56 registers
+__global__ void __launch_bounds__(256 / PX, (PX == 4 && !GSR_BAND_INLINE) ? GSR_BLEND_MINCTAS : 1)
 blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, const uint2 *__restrict__ ranges,
              int width, int height, int tiles_x, int row_begin, const uint32_t *__restrict__ blend_rank,
              uint32_t first_rank, uint32_t last_rank, float *__restrict__ image, float *__restrict__ final_T,
@@ -63,7 +69,7 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   constexpr bool BULK = STAGE == kStageBulk, SOLO = STAGE == kStageWarp;
   constexpr int THREADS = 256 / PX;
   constexpr int WARPS = THREADS / 32;
-  constexpr int kBatch = SOLO ? 64 : (PX >= 8 ? 64 : 128);  // records per staged batch
+  constexpr int kBatch = SOLO ? GSR_BLEND_WBATCH : (PX >= 8 ? 64 : 128);  // records per staged batch
   constexpr int GATHERERS = SOLO ? 32 : THREADS;            // threads that share the gather of one batch
   constexpr int PER = kBatch / GATHERERS;                   // records gathered per thread and batch
   constexpr int BUFS = SOLO ? 2 * WARPS : 2;
