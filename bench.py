@@ -41,8 +41,8 @@ import torch  # noqa: E402
 
 FLOP_PER_EVAL = 24.0           # one Gaussian-pixel evaluation
 PREPROCESS_BYTES = {0: 104.0, 1: 140.0, 2: 200.0, 3: 284.0}  # SURVEY: (11 + 3(d+1)^2)*4 in + 48 out, per Gaussian
-KERNELS_PER_FRAME = 9          # preprocess, 4 depth-sort passes (identity passes return at once), emission fused with the
-#                                first tile-sort pass, 1 tile-sort pass, tile ranges, blend (+ 2 memsets, not counted)
+KERNELS_PER_FRAME = 10         # preprocess, 4 depth-sort passes (identity passes return at once), scan+emit, 2 tile-sort
+#                                passes, tile ranges, blend (+ 2 memsets, not counted)
 
 
 def log(*a):

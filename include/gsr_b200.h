@@ -74,14 +74,6 @@ typedef struct gsr_frame_info {
   uint64_t pixel_evals;   /* evaluations executed by pixels that had not yet terminated */
 } gsr_frame_info;
 
-/* Histograms the preprocess kernels hand to the binning stage, one u32 array of GSR_HIST_WORDS words:
- *   [0, 1024)    the four 8-bit digit histograms of the depth keys of the Gaussians the reference's loop blends
- *                (global digit counts of the one-sweep depth sort);
- *   [1024, 1056) the number of kept (Gaussian, tile) pairs by tile id & 31: the bin sizes of the first, 5-bit pass of
- *                the tile sort, which the emission kernel performs while it writes the pairs. */
-#define GSR_TILE_LO_BINS 32
-#define GSR_HIST_WORDS (4 * 256 + GSR_TILE_LO_BINS)
-
 /* Per-Gaussian record consumed by the blend kernel: 3 x float4, 16-byte aligned. */
 #define GSR_REC_FLOATS 12
 /*  [0] mean2d.x  [1] mean2d.y  [2] A = -a/2   [3] C = -c/2     (a, c, b) = sigmas, rasterize.py:404-411
@@ -195,8 +187,8 @@ int gsr_host_renderer_render(gsr_host_renderer *h, const gsr_gaussians *g_host, 
  *                    with one load per Gaussian
  *  rec[n,12]         blend record (written for visible Gaussians only)
  * optional debug outputs (may be NULL): cov3d[n,9], cov2d[n,4] (after cull zeroing), tile_rect_raw[n,4] i32
- * (the reference's compute_covering_bbox result), mean2d_all[n,2]; depth_hist[GSR_HIST_WORDS] u32 (may be NULL) receives
- * the histograms described at GSR_HIST_WORDS (input of gsr_bin). */
+ * (the reference's compute_covering_bbox result), mean2d_all[n,2]; depth_hist[4*256] u32 receives the 8-bit digit
+ * histograms of the depth keys of the Gaussians the reference's loop blends (input of gsr_bin's one-sweep sort). */
 int gsr_preprocess_fwd(const gsr_gaussians *g, const gsr_camera *cam, int32_t tile_row_begin, int32_t tile_row_end,
                        uint32_t *depth_key, uint32_t *tiles_touched, uint32_t *tile_span, float *rec, float *cov3d,
                        float *cov2d, int32_t *tile_rect_raw, float *mean2d_all, uint32_t *depth_hist, void *stream);
@@ -215,8 +207,8 @@ int gsr_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32_t 
 
 /* Binning: global stable depth sort (:424-425, ties by Gaussian index), duplication into (tile, Gaussian) pairs
  * in depth order, stable sort by tile, tile range extraction.  Equivalent to sorting 64-bit (tile|depth) keys.
- *  depth_hist[GSR_HIST_WORDS] u32 histograms as written by gsr_preprocess_fwd (in, may be NULL: the depth-key digits
- *                     are then counted here and the pairs are sorted by two ordinary passes instead of the fused one)
+ *  depth_hist[4*256]  u32 digit histograms of the blended Gaussians' depth keys as written by gsr_preprocess_fwd
+ *                     (in, may be NULL: they are then counted here)
  *  tile_span[n,4]     u32 tile rect + keep mask as written by gsr_preprocess_fwd (in)
  *  depth_order[n]     u32 ids of the Gaussians the reference's loop blends, in ascending depth; only the first
  *                     info_dev->n_visible entries are written            (out, may be NULL: kept in the workspace)

@@ -40,7 +40,7 @@ static int frame_layout(int64_t n, int width, int height, int64_t max_dup, Frame
   L->rec = take(sizeof(float) * GSR_REC_FLOATS * n1);
   L->order = take(4 * n1);
   L->blend_rank = take(4 * n1);
-  L->depth_hist = take(4 * GSR_HIST_WORDS);
+  L->depth_hist = take(4 * 1024);
   L->tile_ranges = take(8 * (size_t)tg.tiles_x * tg.tiles_y);
   L->tile_gids = take(4 * d1);
   L->zero_a_bytes = L->tile_gids - L->depth_hist;

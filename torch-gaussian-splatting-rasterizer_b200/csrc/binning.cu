@@ -18,8 +18,6 @@
 //
 // The number of pairs never travels to the host: it is left in device memory (clamped to the caller's capacity,
 // overflow flagged in gsr_frame_info.status) and every later kernel reads it from there.
-#include <stdlib.h>
-
 #include "gsr_math.cuh"
 
 namespace gsr {
@@ -279,327 +277,6 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
   }
 }
 
-// ---- emission fused with the FIRST pass of the tile sort -------------------------------------------------------------
-// The pairs leave this kernel already partitioned by the low 5 bits of their tile id (stable: depth order is kept inside
-// a bin), so the tile sort needs one pass less - one full read and write of the pair arrays, one kernel and its
-// look-back.  What a radix pass needs and an emission kernel does not have is the size of every bin BEFORE the first
-// pair is written; the preprocess kernels count it while they cull (hist[1024 + (tile & 31)], include/gsr_b200.h).
-// A CTA (1024 Gaussians in depth order) then works like a one-sweep tile:
-//   1. pair counts, CTA-relative prefix (as in scan_emit_kernel);
-//   2. every lane expands its Gaussians into the warp's staging region: one word per pair, tile << 10 | slot in the CTA;
-//   3. per-warp digit counts by ballot matching (5 ballots per 32 pairs), prefix over the warps and the digits, and the
-//      CTA's 32 bin counts are PUBLISHED for the decoupled look-back;
-//   4. the matching is run again with running counters: every pair goes to its place in the CTA-local sorted buffer;
-//   5. warp 0 walks back over its predecessors (one per step and bin; they are almost always inclusive by now);
-//   6. runs of equal digits leave coalesced: tile ids, Gaussian ids, and the histogram of the next pass's digit.
-// CTAs whose pairs do not fit the staging buffers (a splat covering hundreds of tiles) take a slow path that finds the
-// owner of every pair by binary search and ranks 256 pairs at a time.
-constexpr int kLoBits = 5, kLoBins = 1 << kLoBits;
-static_assert(kLoBins == GSR_TILE_LO_BINS && kLoBins == 32, "one lane per bin");
-constexpr int kSlotBits = 10;                         // slot of a Gaussian in its CTA (kScanTile = 1024)
-constexpr int kCtaCap = kStageCap * (kScanThreads / 32);  // staged pairs per CTA
-static_assert(kScanTile == (1 << kSlotBits) && kTileBitsMax + kSlotBits <= 32, "a staged pair is one word");
-
-// lanes of the warp whose 5-bit digit equals the caller's; lanes with live == false only match each other
-__device__ __forceinline__ uint32_t match_lo(uint32_t d, bool live) {
-  uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
-  peers = live ? peers : ~peers;
-#pragma unroll
-  for (int b = 0; b < kLoBits; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, bit);
-    peers &= bit ? vote : ~vote;
-  }
-  return peers;
-}
-
-__global__ void __launch_bounds__(kScanThreads, 3)
-scan_emit_lo_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ order_x0, uint32_t *__restrict__ order_x1,
-                    const uint32_t *__restrict__ hist /* GSR_HIST_WORDS */, const uint4 *__restrict__ span, int tiles_x,
-                    unsigned long long capacity, unsigned long long *status /* [CTAs][32] */, BinCounters *ctr,
-                    uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids, uint32_t *__restrict__ blend_rank,
-                    uint32_t *__restrict__ tile_hist /* [2][256]: digits of tile >> 5 */, gsr_frame_info *info) {
-  __shared__ unsigned long long s_warp[kScanThreads / 32];
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_hist[2][256];
-  __shared__ uint32_t s_wcnt[kScanThreads / 32][kLoBins];   // pairs of warp w with digit d, then running counters
-  __shared__ uint32_t s_wexcl[kScanThreads / 32][kLoBins];  // ... of the warps before w
-  __shared__ uint32_t s_dexcl[kLoBins + 1];                 // CTA pairs with a smaller digit
-  __shared__ unsigned long long s_gbase[kLoBins];           // first global slot of the CTA's run of digit d
-  extern __shared__ uint32_t s_dyn[];  // stage[kCtaCap] | sorted[kCtaCap] | gid[kScanTile]; the slow path's offsets alias `sorted`
-  uint32_t *stage = s_dyn, *sorted = s_dyn + kCtaCap, *s_gid = sorted + kCtaCap, *s_off = sorted;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
-  s_hist[0][tid] = 0;
-  s_hist[1][tid] = 0;
-  (&s_wcnt[0][0])[tid] = 0;  // kScanThreads == 8 * 32
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const int64_t n = (int64_t)*n_dev;
-  if ((int64_t)tile * kScanTile >= n && tile != 0) return;
-  const int64_t first = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
-  const bool from_x0 = n > 0 && sorted_buffer_index(hist, 4, (uint32_t)n) == 0;  // adaptive depth sort (sort.cu)
-  const uint32_t *order = from_x0 ? order_x0 : order_x1;
-
-  uint32_t gid[kScanItems], cnt[kScanItems];
-  uint4 sp[kScanItems];
-#pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
-    gid[j] = first + j < n ? __ldg(order + first + j) : 0xFFFFFFFFu;
-    sp[j] = make_uint4(0u, 0u, 0u, 0u);
-  }
-#pragma unroll
-  for (int j = 0; j < kScanItems; ++j)
-    if (gid[j] != 0xFFFFFFFFu) sp[j] = __ldg(span + gid[j]);
-  if (from_x0) {
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j)
-      if (gid[j] != 0xFFFFFFFFu) order_x1[first + j] = gid[j];
-  }
-  unsigned long long mine = 0;
-#pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
-    cnt[j] = span_pairs(decode_span(sp[j]));
-    mine += cnt[j];
-  }
-  unsigned long long inc = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-    if (lane >= o) inc += up;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  unsigned long long pre = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
-    if (w < warp) pre += s_warp[w];
-    total += s_warp[w];
-  }
-  const bool fits = total <= (unsigned long long)kCtaCap;  // the CTA's pairs fit the staging buffers
-  const unsigned long long thread_rel = pre + inc - mine;  // pairs of this CTA before this thread's first Gaussian
-  const uint32_t P = (uint32_t)(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
-  // the staged pairs [0, P) are cut into eight consecutive slices, one per warp (multiples of 32, so that the ranking
-  // order - slice, then position - is the staging order, i.e. depth order)
-  const uint32_t slice = ((P + 8 * 32 - 1) / (8 * 32)) * 32;
-  const uint32_t s_begin = min(P, (uint32_t)warp * slice), s_end = min(P, s_begin + slice);
-  if (blend_rank) {
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j)
-      if (gid[j] != 0xFFFFFFFFu) blend_rank[gid[j]] = (uint32_t)(first + j);
-  }
-#pragma unroll
-  for (int j = 0; j < kScanItems; ++j) s_gid[tid * kScanItems + j] = gid[j];
-
-  if (fits) {
-    // ---- 2. expansion: the CTA's pairs, in depth order, into the staging buffer ----
-    uint32_t off = (uint32_t)thread_rel;
-#pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-      if (cnt[j]) {
-        const Span r = decode_span(sp[j]);
-        const uint32_t slot = (uint32_t)(tid * kScanItems + j);
-        const uint32_t origin = r.y0 * (uint32_t)tiles_x + r.x0;
-        if (r.area <= (uint32_t)kCullMaxTiles) {
-          unsigned long long m = r.mask;
-          const uint32_t inv = (65536u + r.w - 1u) / r.w;  // exact row = bit / w for bit < 64
-          while (m) {
-            const uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
-            m &= m - 1;
-            const uint32_t row = (bit * inv) >> 16, col = bit - row * r.w;
-            stage[off++] = ((origin + row * (uint32_t)tiles_x + col) << kSlotBits) | slot;
-          }
-        } else {
-          for (uint32_t ty = 0; ty < r.h; ++ty)
-            for (uint32_t tx = 0; tx < r.w; ++tx) stage[off++] = ((origin + ty * (uint32_t)tiles_x + tx) << kSlotBits) | slot;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- 3. digit counts of this warp's slice (the lowest lane of a group of equal digits adds the group's size) ----
-    for (uint32_t e0 = s_begin; e0 < s_end; e0 += 32) {
-      const bool live = e0 + lane < s_end;
-      const uint32_t d = live ? (stage[e0 + lane] >> kSlotBits) & (kLoBins - 1) : 0u;
-      const uint32_t peers = match_lo(d, live);
-      if (live && lane == __ffs(peers) - 1) s_wcnt[warp][d] += (uint32_t)__popc(peers);
-      __syncwarp();
-    }
-  } else {
-    // slow path, counting sweep: owner of every pair by binary search over the per-Gaussian offsets
-    {
-      unsigned long long run = thread_rel;
-#pragma unroll
-      for (int j = 0; j < kScanItems; ++j) {
-        s_off[tid * kScanItems + j] = (uint32_t)(run < 0xFFFFFFFFull ? run : 0xFFFFFFFFull);
-        run += cnt[j];
-      }
-    }
-    __syncthreads();
-    for (uint32_t e = tid; e < P; e += kScanThreads) {
-      int lo = 0, hi = kScanTile - 1;  // last slot with s_off[slot] <= e
-#pragma unroll
-      for (int it = 0; it < kSlotBits; ++it) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
-      }
-      const Span r = decode_span(__ldg(span + s_gid[lo]));
-      uint32_t local = e - s_off[lo];
-      if (r.area <= (uint32_t)kCullMaxTiles) local = nth_set_bit((uint32_t)r.mask, (uint32_t)(r.mask >> 32), local);
-      const uint32_t row = local / r.w, col = local - row * r.w;
-      atomicAdd(&s_wcnt[0][((r.y0 + row) * (uint32_t)tiles_x + r.x0 + col) & (kLoBins - 1)], 1u);  // order is irrelevant for a count
-    }
-  }
-  __syncthreads();
-  // ---- prefix over warps and digits; publish the CTA's bin counts ----
-  if (warp == 0) {
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) {
-      const uint32_t c = s_wcnt[w][lane];
-      s_wexcl[w][lane] = run;
-      s_wcnt[w][lane] = 0;  // becomes the running counter of the ranking sweep
-      run += c;
-    }
-    st_volatile_u64(status + (size_t)tile * kLoBins + lane, (tile == 0 ? kScanInclusive : kScanAggregate) | run);
-    uint32_t incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    s_dexcl[lane] = incl - run;
-    if (lane == 31) s_dexcl[kLoBins] = incl;
-    // global base of every bin: exclusive prefix of the bin sizes the preprocess kernel counted
-    unsigned long long gb = __ldg(hist + 1024 + lane), gincl = gb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, gincl, o);
-      if (lane >= o) gincl += up;
-    }
-    s_gbase[lane] = gincl - gb;  // + the look-back prefix, below
-    const unsigned long long all = __shfl_sync(0xFFFFFFFFu, gincl, 31);
-    const int64_t tiles_total = n > 0 ? (n + kScanTile - 1) / kScanTile : 1;
-    if (lane == 0 && (int64_t)tile == tiles_total - 1) {  // any one CTA reports the totals: they are known up front here
-      ctr->n_dup = (uint32_t)(all < capacity ? all : capacity);
-      if (info) {
-        const uint32_t dup32 = all < 0xFFFFFFFFull ? (uint32_t)all : 0xFFFFFFFFu;
-        info->n_dup = dup32;
-        info->n_visible = (uint32_t)n;
-        atomicMax(&info->n_dup_peak, dup32);
-        if (all > capacity) info->status = GSR_ERR_DUP_OVERFLOW;
-      }
-    }
-  }
-  __syncthreads();
-  if (!fits) {  // the slow path's per-chunk counts live in s_wexcl and start from zero
-    (&s_wexcl[0][0])[tid] = 0;
-    __syncthreads();
-  }
-  if (fits) {
-    // ---- 4. ranking sweep: every pair to its place in the CTA-local sorted buffer ----
-    for (uint32_t e0 = s_begin; e0 < s_end; e0 += 32) {
-      const bool live = e0 + lane < s_end;
-      const uint32_t entry = live ? stage[e0 + lane] : 0u;
-      const uint32_t d = (entry >> kSlotBits) & (kLoBins - 1);
-      const uint32_t peers = match_lo(d, live);
-      const int leader = __ffs(peers) - 1;
-      uint32_t before = 0;
-      if (live && lane == leader) before = s_wcnt[warp][d];
-      before = __shfl_sync(0xFFFFFFFFu, before, leader);
-      if (live && lane == leader) s_wcnt[warp][d] = before + (uint32_t)__popc(peers);
-      if (live) sorted[s_dexcl[d] + s_wexcl[warp][d] + before + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = entry;
-      __syncwarp();
-    }
-  }
-  // ---- 5. decoupled look-back, one bin per lane ----
-  if (warp == 0) {
-    unsigned long long prefix = 0;
-    if (tile != 0) {
-      int64_t p = (int64_t)tile - 1;
-      while (true) {
-        unsigned long long v = ld_volatile_u64(status + (size_t)p * kLoBins + lane);
-        while ((v >> 62) == 0) {
-          __nanosleep(40);
-          v = ld_volatile_u64(status + (size_t)p * kLoBins + lane);
-        }
-        prefix += v & kScanValue;
-        if ((v & kScanInclusive) || p == 0) break;
-        --p;
-      }
-      const unsigned long long mine_cnt = s_dexcl[lane + 1] - s_dexcl[lane];
-      st_volatile_u64(status + (size_t)tile * kLoBins + lane, kScanInclusive | (prefix + mine_cnt));
-    }
-    s_gbase[lane] += prefix;
-  }
-  __syncthreads();
-  if (fits) {
-    // ---- 6. runs of equal digits leave coalesced ----
-    for (uint32_t j = tid; j < P; j += kScanThreads) {
-      const uint32_t entry = sorted[j], tile_id = entry >> kSlotBits, d = tile_id & (kLoBins - 1);
-      const unsigned long long out = s_gbase[d] + (j - s_dexcl[d]);
-      if (out < capacity) {
-        tile_keys[out] = tile_id;
-        tile_gids[out] = s_gid[entry & (kScanTile - 1)];
-        atomicAdd(&s_hist[0][(tile_id >> kLoBits) & 255u], 1u);
-        atomicAdd(&s_hist[1][tile_id >> (kLoBits + 8)], 1u);
-      }
-    }
-  } else {
-    // slow path, ranking sweep: 256 consecutive pairs at a time (one per thread), ranked in (warp, lane) order
-    for (uint32_t e0 = 0; e0 < P; e0 += kScanThreads) {
-      const uint32_t e = e0 + tid;
-      const bool live = e < P;
-      uint32_t tile_id = 0, g_id = 0;
-      if (live) {
-        int lo = 0, hi = kScanTile - 1;
-#pragma unroll
-        for (int it = 0; it < kSlotBits; ++it) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
-        }
-        g_id = s_gid[lo];
-        const Span r = decode_span(__ldg(span + g_id));
-        uint32_t local = e - s_off[lo];
-        if (r.area <= (uint32_t)kCullMaxTiles) local = nth_set_bit((uint32_t)r.mask, (uint32_t)(r.mask >> 32), local);
-        const uint32_t row = local / r.w, col = local - row * r.w;
-        tile_id = (r.y0 + row) * (uint32_t)tiles_x + r.x0 + col;
-      }
-      const uint32_t d = tile_id & (kLoBins - 1);
-      const uint32_t peers = match_lo(d, live);
-      if (live && lane == __ffs(peers) - 1) s_wexcl[warp][d] = (uint32_t)__popc(peers);  // this warp's count of d in the chunk
-      __syncthreads();
-      uint32_t before = 0;  // pairs of this chunk with my digit in the warps before mine
-      if (live) {
-        for (int w = 0; w < warp; ++w) before += s_wexcl[w][d];
-        const unsigned long long out = s_gbase[d] + s_wcnt[0][d] + before + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        if (out < capacity) {
-          tile_keys[out] = tile_id;
-          tile_gids[out] = g_id;
-          atomicAdd(&s_hist[0][(tile_id >> kLoBits) & 255u], 1u);
-          atomicAdd(&s_hist[1][tile_id >> (kLoBits + 8)], 1u);
-        }
-      }
-      __syncthreads();
-      if (warp == 0) {  // running counters += the chunk's counts; per-warp counts back to zero
-        uint32_t add = 0;
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) {
-          add += s_wexcl[w][lane];
-          s_wexcl[w][lane] = 0;
-        }
-        s_wcnt[0][lane] += add;
-      }
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint32_t v = s_hist[q][tid];
-    if (v) atomicAdd(tile_hist + q * 256 + tid, v);
-  }
-}
-
 // [begin, end) of every tile's list, read off the sorted tile ids: position i opens the list of its tile when the
 // id differs from its left neighbour's and closes it when it differs from the right one's.  Tiles without pairs keep
 // the (0, 0) the caller memset.
@@ -645,7 +322,7 @@ static BinLayout bin_layout(int64_t n, int64_t max_dup) {
   };
   const int64_t n1 = n > 0 ? n : 1, d1 = max_dup > 0 ? max_dup : 1;
   L.counters = take(sizeof(BinCounters));
-  L.scan_status = take(sizeof(unsigned long long) * kLoBins * (size_t)ceil_div64(n1, kScanTile));  // [CTAs][32] look-back words
+  L.scan_status = take(sizeof(unsigned long long) * (size_t)ceil_div64(n1, kScanTile));
   L.tile_hist = take(sizeof(uint32_t) * 4 * 256);
   L.depth_sort = take(sort_scratch_bytes(n1));
   L.tile_sort = take(sort_scratch_bytes(d1));
@@ -731,45 +408,23 @@ int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hi
   const uint32_t *depth_hist_used = depth_hist ? depth_hist : s1.hist;
   if (rc) return rc;
 
-  // 2. + 3.  Pair emission in depth order and the stable sort of the pairs by tile id.
+  // 2. prefix scan of the pair counts in depth order + pair emission + digit histograms of the tile ids
   uint32_t *tkeys_a = (uint32_t *)(ws + L.tkeys_a), *tgids_a = (uint32_t *)(ws + L.tgids_a);
-  uint32_t *sorted_tiles = (uint32_t *)(ws + L.tkeys_c);
+  const size_t stage_bytes = sizeof(uint32_t) * kStageWords * (kScanThreads / 32);
+  scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, stage_bytes, stream>>>(
+      vis_count, (const uint32_t *)(ws + L.dvals_tmp), depth_order, depth_hist_used, (const uint4 *)tile_span, tg.tiles_x,
+      (unsigned long long)max_dup, scan_status, ctr, tkeys_a,
+      tgids_a, blend_rank, tile_hist, info_dev);
+  GSR_LAUNCH_CHECK();
+
+  // 3. stable sort of the pairs by tile id
   rc = sort_scratch_carve(ws + L.tile_sort, L.order - L.tile_sort, max_dup, &s2);
   if (rc) return rc;
-  // GSR_BIN_FUSED=0 forces the two-pass route (A/B measurements); without the preprocess kernels' histograms it is the
-  // only route (the bin sizes of the fused pass come from there)
-  static const bool allow_fused = [] {
-    const char *e = getenv("GSR_BIN_FUSED");
-    return !(e && e[0] == '0');
-  }();
-  if (depth_hist && allow_fused) {
-    // fused: the emission kernel also performs the first (5-bit) pass of the tile sort; what is left are the bits above
-    const size_t smem = sizeof(uint32_t) * (2 * (size_t)kCtaCap + kScanTile);
-    GSR_CHECK_CUDA(ensure_dynamic_smem<&scan_emit_lo_kernel>((int)smem));
-    scan_emit_lo_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, smem, stream>>>(
-        vis_count, (const uint32_t *)(ws + L.dvals_tmp), depth_order, depth_hist, (const uint4 *)tile_span, tg.tiles_x,
-        (unsigned long long)max_dup, scan_status, ctr, tkeys_a, tgids_a, blend_rank, tile_hist, info_dev);
-    GSR_LAUNCH_CHECK();
-    if (tile_bits > kLoBits) {
-      rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),
-                             (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, kLoBits, tile_bits, s2, stream, false,
-                             tile_hist, nullptr, nullptr, true, false);
-      if (rc) return rc;
-    } else {  // at most 32 tiles: the fused pass has sorted them completely
-      GSR_CHECK_CUDA(cudaMemcpyAsync(tile_gids, tgids_a, sizeof(uint32_t) * (size_t)max_dup, cudaMemcpyDeviceToDevice, stream));
-      sorted_tiles = tkeys_a;
-    }
-  } else {
-    const size_t stage_bytes = sizeof(uint32_t) * kStageWords * (kScanThreads / 32);
-    scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, stage_bytes, stream>>>(
-        vis_count, (const uint32_t *)(ws + L.dvals_tmp), depth_order, depth_hist_used, (const uint4 *)tile_span, tg.tiles_x,
-        (unsigned long long)max_dup, scan_status, ctr, tkeys_a, tgids_a, blend_rank, tile_hist, info_dev);
-    GSR_LAUNCH_CHECK();
-    rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),
-                           (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false, tile_hist, nullptr,
-                           nullptr, true, false);
-    if (rc) return rc;
-  }
+  uint32_t *sorted_tiles = (uint32_t *)(ws + L.tkeys_c);
+  rc = launch_sort_pairs(tkeys_a, tgids_a, sorted_tiles, tile_gids, (uint32_t *)(ws + L.tkeys_b),
+                         (uint32_t *)(ws + L.tgids_b), max_dup, &ctr->n_dup, 0, tile_bits, s2, stream, false, tile_hist, nullptr,
+                         nullptr, true, false);
+  if (rc) return rc;
 
   // 4. tile ranges from the sorted ids
   const int64_t want = ceil_div64(max_dup, kRangeThreads * 4);  // four ids per thread

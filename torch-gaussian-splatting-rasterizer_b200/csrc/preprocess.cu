@@ -29,10 +29,8 @@ constexpr int kPreThreads = 256;
 //   C  per lane : SH colour + blend record, only for Gaussians that keep at least one tile
 // It also accumulates the four 8-bit digit histograms of the depth keys (global digit counts of the one-sweep
 // sort) in shared memory; the kernels flush them once per CTA.
-constexpr int kHistWords = 4 * 256 + GSR_TILE_LO_BINS;  // depth-key digit counts + low-digit counts of the kept tile ids
 struct PreShared {
   uint32_t hist[4][256];
-  uint32_t lo_hist[GSR_TILE_LO_BINS];   // kept (Gaussian, tile) pairs by tile id & 31: bin sizes of the binning stage's first pass
   CullGaussian cg[kPreThreads / 32][32];
   int4 rect[kPreThreads / 32][32];      // x0, y0, width, 2^16/width rounded up (0 when the rect is empty)
   uint32_t mask[kPreThreads / 32][32][2];
@@ -151,7 +149,6 @@ __device__ __forceinline__ void pre_body(PreShared &sm, const gsr_camera &cam, c
       // Lanes that test candidates of the same owner form one contiguous run of the warp (candidates are ordered by
       // owner); the first lane of each run ORs the run's keep bits into the owner's mask - no shared atomics.
       const bool keep = valid && !tile_is_empty(sm.cg[warp][lo], px0, py0, px1, py1);
-      if (HIST && keep) atomicAdd(&sm.lo_hist[((r.y + row) * tg.tiles_x + r.x + col) & (GSR_TILE_LO_BINS - 1)], 1u);
       const uint32_t kept = __ballot_sync(0xFFFFFFFFu, keep);
       const int prev_lo = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
       const uint32_t heads = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev_lo != lo);
@@ -172,11 +169,6 @@ __device__ __forceinline__ void pre_body(PreShared &sm, const gsr_camera &cam, c
     mask_lo = sm.mask[warp][lane][0];
     mask_hi = sm.mask[warp][lane][1];
     tiles = (uint32_t)(__popc(mask_lo) + __popc(mask_hi));
-  }
-  if (HIST && !cand && area > 0) {  // rects that keep every tile (strips, rects above 64 tiles, ill-conditioned conics)
-    for (int ty = 0; ty < h; ++ty)
-      for (int tx = 0; tx < w; ++tx)
-        atomicAdd(&sm.lo_hist[((y0 + ty) * tg.tiles_x + x0 + tx) & (GSR_TILE_LO_BINS - 1)], 1u);
   }
   __syncwarp();  // shared arrays are rewritten by the next iteration
 
@@ -235,7 +227,7 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
   __shared__ PreShared sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (depth_hist) {
-    for (int k = threadIdx.x; k < kHistWords; k += kPreThreads) (&sm.hist[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&sm.hist[0][0])[k] = 0;
     __syncthreads();
   }
   constexpr int degree = DEGREE;
@@ -287,7 +279,7 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
   }
   if (depth_hist) {
     __syncthreads();
-    for (int k = threadIdx.x; k < kHistWords; k += kPreThreads) {
+    for (int k = threadIdx.x; k < 1024; k += kPreThreads) {
       const uint32_t v = (&sm.hist[0][0])[k];
       if (v) atomicAdd(depth_hist + k, v);
     }
@@ -362,7 +354,7 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
                            uint4 *__restrict__ span_out, float4 *__restrict__ rec, uint32_t *__restrict__ depth_hist) {
   __shared__ PreShared sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = threadIdx.x; k < kHistWords; k += kPreThreads) (&sm.hist[0][0])[k] = 0;
+  for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&sm.hist[0][0])[k] = 0;
   __syncthreads();
   constexpr int ncoef = (DEGREE + 1) * (DEGREE + 1);
   constexpr int rows = (ncoef + 3) / 4;  // float4 rows per channel that hold coefficients of this degree
@@ -436,7 +428,7 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
                    rec, dbg, colour);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < kHistWords; k += kPreThreads) {
+  for (int k = threadIdx.x; k < 1024; k += kPreThreads) {
     const uint32_t v = (&sm.hist[0][0])[k];
     if (v) atomicAdd(depth_hist + k, v);
   }
@@ -573,7 +565,7 @@ int gsr::preprocess_raw(const gsr_gaussians *g, const gsr_camera *cam, int32_t r
               "image size out of range");
   GSR_REQUIRE(depth_key && tiles_touched && tile_span && rec, "null output");
   GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)tile_span & 15) == 0, "rec and tile_span must be 16-byte aligned");
-  if (depth_hist && !hist_zeroed) GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * GSR_HIST_WORDS, stream));
+  if (depth_hist && !hist_zeroed) GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * 1024, stream));
   if (g->n == 0) return GSR_OK;
   unsigned blocks = blocks_for(g->n, kPreThreads);
   const unsigned resident = (unsigned)sm_count() * 4;  // persistent: a few CTAs per SM, each loops over its share
@@ -627,7 +619,7 @@ extern "C" int gsr_preprocess_prepared_fwd(const void *prepared, int64_t n, cons
   GSR_REQUIRE(depth_key && tiles_touched && tile_span && rec && depth_hist, "null output");
   GSR_REQUIRE(((uintptr_t)rec & 15) == 0 && ((uintptr_t)tile_span & 15) == 0 && ((uintptr_t)prepared & 255) == 0,
               "rec / tile_span must be 16-byte aligned, prepared 256-byte aligned");
-  GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * GSR_HIST_WORDS, (cudaStream_t)stream));
+  GSR_CHECK_CUDA(cudaMemsetAsync(depth_hist, 0, sizeof(uint32_t) * 1024, (cudaStream_t)stream));
   if (n == 0) return GSR_OK;
   return launch_preprocess_prepared(prepared, n, cam, row_begin, row_end, depth_key, tiles_touched, tile_span, rec,
                                     depth_hist, (cudaStream_t)stream);

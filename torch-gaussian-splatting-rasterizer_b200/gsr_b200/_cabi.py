@@ -16,7 +16,6 @@ LIB_PATH = os.environ.get("GSR_B200_LIB") or os.path.join(PKG, "csrc", "libgsr_b
 
 GSR_OK, GSR_ERR_INVALID_ARGUMENT, GSR_ERR_CUDA, GSR_ERR_WORKSPACE_TOO_SMALL, GSR_ERR_DUP_OVERFLOW = range(5)
 REC_FLOATS = 12
-HIST_WORDS = 4 * 256 + 32  # GSR_HIST_WORDS: depth-key digit histograms + low-digit histogram of the kept tile ids
 TILE = 16
 
 

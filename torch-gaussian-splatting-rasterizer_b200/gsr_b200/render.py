@@ -558,7 +558,7 @@ def preprocess(model: GaussianModel, cam: CameraStruct, debug: bool = False, til
                tiles_touched=torch.empty(n, dtype=torch.int32, device=dev),
                tile_span=torch.zeros((n, 4), dtype=torch.int32, device=dev),
                rec=torch.zeros((n, _cabi.REC_FLOATS), dtype=torch.float32, device=dev),
-               depth_hist=torch.empty(_cabi.HIST_WORDS, dtype=torch.int32, device=dev))
+               depth_hist=torch.empty(1024, dtype=torch.int32, device=dev))
     if debug:
         out.update(cov3d=torch.empty((n, 3, 3), dtype=torch.float32, device=dev),
                    cov2d=torch.empty((n, 2, 2), dtype=torch.float32, device=dev),
@@ -593,7 +593,7 @@ class Stages:
         i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
         self.depth_key, self.tiles_touched, self.tile_span = i32(max(n, 1)), i32(max(n, 1)), i32(max(n, 1), 4)
         self.rec = torch.zeros((max(n, 1), _cabi.REC_FLOATS), dtype=torch.float32, device=dev)
-        self.depth_hist, self.order, self.blend_rank = i32(_cabi.HIST_WORDS), i32(max(n, 1)), i32(max(n, 1))
+        self.depth_hist, self.order, self.blend_rank = i32(1024), i32(max(n, 1)), i32(max(n, 1))
         self.tile_gids = i32(self.max_dup)
         self.tile_ranges = i32(((width + 15) // 16) * ((height + 15) // 16), 2)
         self.info = torch.zeros(8, dtype=torch.int32, device=dev)
