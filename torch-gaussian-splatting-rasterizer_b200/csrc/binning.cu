@@ -73,7 +73,10 @@ __device__ __forceinline__ uint32_t span_pairs(const Span &s) {
 
 // Walks the compacted depth order: prefix scan of the pair counts (decoupled look-back across CTAs), emission of the
 // (tile id, Gaussian id) pairs in depth order, blend ranks, and the digit histograms of the tile ids.
-__global__ void __launch_bounds__(kScanThreads, 4)
+#ifndef GSR_SCAN_MINCTAS
+#define GSR_SCAN_MINCTAS 4
+#endif
+__global__ void __launch_bounds__(kScanThreads, GSR_SCAN_MINCTAS)
 scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ order_x0, uint32_t *__restrict__ order_x1,
                  const uint32_t *__restrict__ depth_hist, const uint4 *__restrict__ span,
                  int tiles_x, unsigned long long capacity, unsigned long long *status, BinCounters *ctr,
