@@ -31,9 +31,6 @@
 #ifndef GSR_BLEND_MINCTAS
 #define GSR_BLEND_MINCTAS 18  // resident CTAs per SM the 4-pixel kernel is compiled for (18: <= 56 registers)
 #endif
-#ifndef GSR_BLEND_PIPE
-#define GSR_BLEND_PIPE 0
-#endif
 #ifndef GSR_BLEND_GROUP
 #define GSR_BLEND_GROUP 4   // records walked per warp vote (unrolled); 2 halves the loop body (A/B builds)
 #endif
@@ -233,38 +230,6 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
             for (int k = 0; k < PX; ++k) my_evals += fy[k] < 0.5f * kParkedY;
           }
       }
-#if GSR_BLEND_PIPE
-      // software pipeline of depth one: the powers of record u+1 are evaluated before record u is blended, so that
-      // their dependent FP32 chain overlaps the blend branch.  A pixel that record u terminates has a stale (valid
-      // looking) power for record u+1: the blend condition therefore also asks for T >= 1e-4.
-      float pw[2][PX], th[2];
-      bool an[2];
-      an[0] = powers(base + j * GSR_REC_FLOATS, pw[0], th[0]);
-#pragma unroll
-      for (int u = 0; u < GSR_BLEND_GROUP; ++u) {
-        const int c = u & 1, nx = c ^ 1;
-        if (u + 1 < GSR_BLEND_GROUP) an[nx] = powers(base + (j + u + 1) * GSR_REC_FLOATS, pw[nx], th[nx]);
-        if (an[c]) {
-          const float *r = base + (j + u) * GSR_REC_FLOATS;
-          const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
-          const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
-          float pmax = pw[c][0];
-#pragma unroll
-          for (int k = 1; k < PX; ++k) pmax = fmaxf(pmax, pw[c][k]);
-          if (pmax <= 0.0f && orr.x < 0.9899f) {
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-              if (pw[c][k] >= th[c] && T[k] >= kStopT)
-                blend_slot_plain(k, pw[c][k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
-          } else {
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-              if (pw[c][k] >= th[c] && T[k] >= kStopT)
-                blend_slot(k, pw[c][k], orr.x, gbl.z, orr.y, gbl.x, gbl.y, list_base + j + u + 1);
-          }
-        }
-      }
-#else
 #pragma unroll
       for (int u = 0; u < GSR_BLEND_GROUP; ++u) {
         const float *r = base + (j + u) * GSR_REC_FLOATS;
@@ -286,7 +251,6 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
           }
         }
       }
-#endif
       // Leave the batch once the whole warp has terminated.  The vote sits at the top level of the loop body, where
       // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
       // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
