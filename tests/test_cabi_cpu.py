@@ -153,3 +153,27 @@ def test_ground_truth_comparison_and_frame_writer_run_on_the_host(tmp_path):
     assert Image.open(tmp_path / "cmp.png").size == (30, 40)  # render above the photo
     n = rasterize.write_frame_sequence(torch.stack([a, b]), str(tmp_path / "seq"))
     assert n == 2 and sorted(p.name for p in (tmp_path / "seq").iterdir()) == ["frame_0000000.png", "frame_0000001.png"]
+
+
+def test_host_struct_layouts():
+    """gsr_b200.render._host_struct: what the host pipeline is handed for each layout of the host tensors - dense rows
+    and planar / dense SH are passed as they are (no copy: the data pointer is the caller's), anything else is made
+    dense first."""
+    import torch
+
+    from gsr_b200 import render as R, scenes
+
+    cloud = scenes.synth_v1(37, 3)
+    xyz, ls, rot, op = (torch.from_numpy(a) for a in (cloud.xyz, cloud.scales, cloud.rots, cloud.opacity))
+    planar = torch.from_numpy(cloud.sh_planar())            # [3,16,N] storage
+    sh_view = planar.permute(2, 1, 0)                        # the reference's [N,16,3] view (utils.py:31)
+    g, keep = R._host_struct(xyz, ls, rot, op, sh_view)
+    assert g.n == 37 and (g.sh_sn, g.sh_sk, g.sh_sc) == (1, 37, 16 * 37) and g.sh == planar.data_ptr()
+    assert g.xyz == xyz.data_ptr() and (g.xyz_sn, g.xyz_sc) == (3, 1) and g.opacity_sn == 1
+    dense = sh_view.contiguous()
+    g, keep = R._host_struct(xyz, ls, rot, op, dense)
+    assert (g.sh_sn, g.sh_sk, g.sh_sc) == (48, 3, 1) and g.sh == dense.data_ptr()
+    odd = torch.zeros((37, 16, 6))[:, :, ::2]                # a strided view that is neither: copied to dense rows
+    g, keep = R._host_struct(xyz.double(), ls, rot[:, :].t().contiguous().t(), op, odd)
+    assert (g.sh_sn, g.sh_sk, g.sh_sc) == (48, 3, 1) and g.sh != odd.data_ptr()
+    assert g.xyz != xyz.data_ptr() and (g.rot_sn, g.rot_sc) == (4, 1)   # float64 / column-major inputs were converted

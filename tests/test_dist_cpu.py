@@ -70,6 +70,42 @@ def _worker(rank, world, port, n_views, H, W):
         dist.destroy_process_group()
 
 
+class _FakeRenderer:
+    """Stands in for gsr_b200.render.Renderer in the overflow agreement: sticky status words held on the host."""
+
+    def __init__(self, status, peak):
+        self.device, self.info, self.max_dup, self.cleared = "cpu", dict(status=status, n_dup_peak=peak), 1000, 0
+
+    def frame_info(self):
+        return dict(self.info)
+
+    def clear_status(self):
+        self.info, self.cleared = dict(status=0, n_dup_peak=0), self.cleared + 1
+
+
+def _overflow_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # nobody overflowed: nothing to do, status untouched
+        r = _FakeRenderer(0, 700)
+        assert gd._agree_on_overflow(r) == 0 and r.cleared == 0
+        # only rank 1 overflowed (a frame in the middle of its sequence needed 5000 pairs): EVERY rank must learn the
+        # same capacity, or the ranks would take different branches around the collective that follows
+        r = _FakeRenderer(4 if rank == 1 else 0, 5000 if rank == 1 else 800)
+        cap = gd._agree_on_overflow(r)
+        assert cap == int(5000 * 1.1) + 1024 and r.cleared == 1 and r.frame_info()["status"] == 0
+        # both overflowed: the larger need wins
+        r = _FakeRenderer(4, 3000 + 1000 * rank)
+        assert gd._agree_on_overflow(r) == int(4000 * 1.1) + 1024
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overflow_status_is_agreed_across_ranks():
+    mp.spawn(_overflow_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("n_views,H,W", [(5, 40, 24), (4, 33, 16)])
 def test_two_rank_gloo_gathers(n_views, H, W):
     mp.spawn(_worker, args=(2, _free_port(), n_views, H, W), nprocs=2, join=True)
