@@ -727,6 +727,17 @@ def main():
                 copied[b] = torch.cuda.Event(); copied[b].record(copy_stream)
         torch.cuda.synchronize()
 
+    # the PCIe floor of this box, measured: the same bytes as ONE monolithic pinned copy (no kernel, no read-back)
+    floor_src = torch.empty(h2d // 4, dtype=torch.float32).pin_memory()
+    floor_dst = torch.empty(h2d // 4, dtype=torch.float32, device="cuda")
+
+    def h2d_floor(n):
+        for _ in range(n):
+            floor_dst.copy_(floor_src, non_blocking=True)
+            torch.cuda.synchronize()
+
+    dt_floor = wall(h2d_floor, 4)
+    del floor_src, floor_dst
     dt = wall(pipelined, args.e2e_steps)
     dt_sync = wall(one_at_a_time, max(3, args.e2e_steps // 2))
     dt_res = wall(resident, 4 * args.e2e_steps)
@@ -740,6 +751,9 @@ def main():
                                "chunk as it lands - no prepared copy, so nothing is amortised), 2 frames in flight; PCIe-bound: "
                                "708 MB per frame is ~13 ms at ~54 GB/s, i.e. the 100 fps target is defined on the resident "
                                "scene; whole-job sum, max over ranks",
+                       "h2d_floor_ms": dt_floor * 1e3, "h2d_floor_gbs": h2d / dt_floor / 1e9,
+                       "h2d_floor_what": "one monolithic pinned copy of the same 708 MB with nothing else running: the PCIe "
+                                         "floor of a host-buffer frame on this box",
                        "one_frame_at_a_time": {"fps": world / dt_sync, "ms_per_step": dt_sync * 1e3,
                                                "what": "same object, submit + wait per frame (latency of one host-buffer frame)"},
                        "resident_scene": {"fps": world / dt_res, "ms_per_step": dt_res * 1e3,
