@@ -611,6 +611,25 @@ def main():
             renderer.render(model, cam, out=frame, check=False)
         evs[1].record(); torch.cuda.synchronize()
         t_single = evs[0].elapsed_time(evs[1]) / reps
+        # forward with contributor tracking + backward (north_star item 4), same frame
+        fT = torch.empty((H, W), device="cuda")
+        nC = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+        Gimg = torch.rand((H, W, 3), device="cuda")
+        rb_ = R.Renderer()
+        rb_.render(model, cam, out=frame, final_T=fT, n_contrib=nC, prepared=False)
+        for _ in range(2):
+            rb_.render(model, cam, out=frame, final_T=fT, n_contrib=nC, check=False, prepared=False)
+            rb_.backward(model, cam, fT, nC, Gimg)
+        torch.cuda.synchronize()
+        evs[0].record()
+        for _ in range(5):
+            rb_.render(model, cam, out=frame, final_T=fT, n_contrib=nC, check=False, prepared=False)
+        evs[1].record()
+        for _ in range(5):
+            rb_.backward(model, cam, fT, nC, Gimg)
+        evs[2].record(); torch.cuda.synchronize()
+        t_fwd_tracked, t_bwd = evs[0].elapsed_time(evs[1]) / 5, evs[1].elapsed_time(evs[2]) / 5
+        del rb_, fT, nC, Gimg
         peak_t, mhz = _cabi.ctypes.c_double(), _cabi.ctypes.c_double()
         _cabi.call("gsr_fp32_fma_peak", _cabi.ctypes.byref(peak_t), _cabi.ctypes.byref(mhz))
         fp32_peak = peak_t.value
@@ -625,10 +644,12 @@ def main():
         pre_bytes_design = (240.0 + 24.0) * cloud.n + 48.0 * n_vis  # prepared rows in; key, flags, span out; records of the visible
         blend_tflops = warp_evals * FLOP_PER_EVAL / (t_blend * 1e-3) / 1e12
         line["stages_ms"] = {"preprocess": t_pre, "binning": t_bin, "blend": t_blend, "single_frame": t_single,
-                             "prepare_once": t_prepare,
+                             "prepare_once": t_prepare, "forward_for_training": t_fwd_tracked, "backward": t_bwd,
                              "note": "one C-ABI call per stage on preallocated buffers, CUDA events on the launching stream; "
                                      "single_frame = one whole frame alone on the GPU (latency); prepare_once = gsr_prepare, "
-                                     "paid once per model (at load), not per frame"}
+                                     "paid once per model (at load), not per frame; forward_for_training = the raw-parameter "
+                                     "frame with contributor tracking, backward = gsr_render_bwd of that frame (blend "
+                                     "backward + preprocess / SH backward, gradients of all 59 parameters per Gaussian)"}
         prof = load_profile("r02_kernel_dram.json") or {}
         bl = prof.get("blend_kernel", {})
         line["roofline"] = {"kernel": "blend_kernel<4,0,0,0,0>", "bound": "fp32_fma", "achieved": blend_tflops, "peak": fp32_peak,
