@@ -199,7 +199,7 @@ with tempfile.TemporaryDirectory() as d:
     t0 = time.time()
     scenes.write_scene_dir(d, cloud, intr, [scenes.front_view(0)])
     t_write = time.time() - t0
-    probe = ref_harness.time_reference(d, 0, max_blended=200)          # cost per blended Gaussian on this host
+    probe = ref_harness.time_reference(d, 0, max_blended=2000)         # cost per blended Gaussian on this host
     per = probe["loop_s"] / max(1, probe["blended"])
     sample = max(200, int(budget / max(per, 1e-6)))
     out = ref_harness.time_reference(d, 0, max_blended=sample)
