@@ -16,11 +16,12 @@
 //
 // Work decomposition: one CTA per tile, 256/PX threads, PX pixels of one column per thread (rows rg*PX..rg*PX+PX-1),
 // so the dx-dependent half of `power` (dx, dx^2, A dx^2, B dx) is computed once per Gaussian and thread.  The tile's
-// list is staged through shared memory in batches of 128 raw 48-byte records with cp.async (LDGSTS), double
-// buffered: the gather of batch b+1 and the index loads of batch b+2 are in flight while batch b is evaluated with
-// broadcast shared-memory reads.  ~90 % of evaluations end at the `power < thr` test (6 floats read per Gaussian and
-// thread, 7 FP32 operations per pixel, no exp).  A CTA leaves as soon as every pixel has terminated; a terminated
-// pixel is parked at y = 1e18 so that it fails the test without costing an extra instruction.
+// list is staged through shared memory in batches of raw 48-byte records with cp.async (LDGSTS), double buffered - by
+// default per WARP, 32 records at a time (STAGE below): the gather of batch b+1 and the index loads of batch b+2 are in
+// flight while batch b is evaluated with broadcast shared-memory reads.  ~90 % of evaluations end at the `power < thr`
+// test (6 floats read per Gaussian and thread, 7 FP32 operations per pixel, no exp).  A warp leaves as soon as every
+// one of its pixels has terminated; a terminated pixel is parked at y = 1e18 so that it fails the test without costing
+// an extra instruction.
 #include <stdlib.h>
 
 #include "blend_common.cuh"
