@@ -100,9 +100,9 @@ int gsr_debug_blend_variant(int stage, int pretest);
  * first_rank/last_rank restrict blending to Gaussians whose global depth rank r satisfies
  * first_rank <= r < last_rank (progressive renders, :448-452); pass 0 and UINT32_MAX for everything.
  * tile_row_begin/end restrict the frame to a band of tile rows (multi-GPU band sharding); rows outside
- * the band are left untouched in image.  The image may have at most 65536 tiles of 16x16 pixels (e.g. 4096x4096; the
- * tile sort is two 8-bit passes) - larger frames are refused with GSR_ERR_INVALID_ARGUMENT.  info_dev (device, may be
- * NULL) receives counters; it is never cleared by
+ * the band are left untouched in image.  Frames of up to 65536 tiles (e.g. 4096x4096) sort their (Gaussian, tile) pairs
+ * in two 8-bit passes, larger ones (8K: 512 x 270 tiles) in three.  info_dev (device, may be NULL) receives counters;
+ * it is never cleared by
  * the library (see gsr_frame_info).  Workspace offsets of everything gsr_render_bwd replays do not depend on max_dup.
  * --------------------------------------------------------------------------------------------- */
 int gsr_render_workspace_bytes(int64_t n, int32_t width, int32_t height, int64_t max_dup, size_t *bytes);

@@ -192,3 +192,13 @@ def test_blend_staging_variants_are_bit_identical():
     for o in outs[1:]:
         for x, y in zip(o, outs[0]):
             assert torch.equal(x, y)
+
+
+def test_frame_above_65536_tiles_takes_three_tile_sort_passes():
+    """An 8K frame (7680x4320 = 480 x 270 = 129600 tiles, 17 tile-id bits): the pair sort needs a third 8-bit pass and a
+    third digit histogram; image against the oracle as at any other size."""
+    cloud = scenes.synth_v1(30_000, 29, scale_factor=0.1)
+    cam = camera.camera_for(scenes.Intrinsics.synthetic(7680, 4320), scenes.front_view(0), 3)
+    img, ref, r = _render_both(cloud, cam)
+    assert np.abs(img - ref["image"]).max() < 2e-4
+    assert img.max() > 0.2 and r.frame_info()["n_visible"] == int((ref["skip"] == 0).sum())

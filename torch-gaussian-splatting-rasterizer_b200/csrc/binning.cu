@@ -27,7 +27,7 @@ constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kStageCap = 1024;  // pairs a warp can stage in shared memory (one word each)
 constexpr int kStageWords = kStageCap + 32 * kScanItems + (32 * kScanItems + 1) + 3;  // + ids + offsets, 16-byte multiple
-constexpr int kTileBitsMax = 16;  // two 8-bit passes of the tile sort; also bounds the packed staging word
+constexpr int kTileBitsMax = 24;  // up to three 8-bit passes of the tile sort; the packed staging word holds tile << 7 | slot
 
 constexpr unsigned long long kScanAggregate = 1ull << 62;
 constexpr unsigned long long kScanInclusive = 2ull << 62;
@@ -81,16 +81,17 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
                  const uint32_t *__restrict__ depth_hist, const uint4 *__restrict__ span,
                  int tiles_x, unsigned long long capacity, unsigned long long *status, BinCounters *ctr,
                  uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ tile_gids, uint32_t *__restrict__ blend_rank,
-                 uint32_t *__restrict__ tile_hist /*[2][256]*/, gsr_frame_info *info) {
+                 uint32_t *__restrict__ tile_hist /*[3][256]*/, int wide_tiles /* more than 65536 tiles */, gsr_frame_info *info) {
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_hist[2][256];
+  __shared__ uint32_t s_hist[3][256];
   extern __shared__ uint32_t s_dyn[];  // per warp: [kStageCap] packed pairs | [128] Gaussian ids | [129] offsets
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&ctr->ticket, 1u);
   s_hist[0][tid] = 0;
   s_hist[1][tid] = 0;
+  s_hist[2][tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t n = (int64_t)*n_dev;  // entries of `order`: the Gaussians the reference's loop blends
@@ -246,7 +247,8 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
         tile_keys[out] = tile_id;
         tile_gids[out] = s_gid[pr & 127u];
         atomicAdd(&s_hist[0][tile_id & 255u], 1u);
-        atomicAdd(&s_hist[1][tile_id >> 8], 1u);
+        atomicAdd(&s_hist[1][(tile_id >> 8) & 255u], 1u);
+        if (wide_tiles) atomicAdd(&s_hist[2][tile_id >> 16], 1u);  // third pass: frames above 65536 tiles (uniform branch)
       }
     }
   } else if (warp_total != 0) {
@@ -269,12 +271,13 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
       tile_keys[warp_out + e] = tile_id;
       tile_gids[warp_out + e] = g_id;
       atomicAdd(&s_hist[0][tile_id & 255u], 1u);
-      atomicAdd(&s_hist[1][tile_id >> 8], 1u);
+      atomicAdd(&s_hist[1][(tile_id >> 8) & 255u], 1u);
+      if (wide_tiles) atomicAdd(&s_hist[2][tile_id >> 16], 1u);
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < 3; ++q) {
     const uint32_t v = s_hist[q][tid];
     if (v) atomicAdd(tile_hist + q * 256 + tid, v);
   }
@@ -375,7 +378,7 @@ int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hi
   const int num_tiles = tg.tiles_x * tg.tiles_y;
   int tile_bits = 1;
   while ((1 << tile_bits) < num_tiles) ++tile_bits;
-  GSR_REQUIRE(tile_bits <= kTileBitsMax, "more than 65536 tiles are not supported by the two-pass tile sort");
+  GSR_REQUIRE(tile_bits <= kTileBitsMax, "more than 2^24 tiles are not supported");
   const BinLayout L = bin_layout(n, max_dup);
   if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("bin workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, L.total);
@@ -417,7 +420,7 @@ int gsr::bin_impl(int64_t n, const uint32_t *depth_key, const uint32_t *depth_hi
   scan_emit_kernel<<<(unsigned)ceil_div64(n, kScanTile), kScanThreads, stage_bytes, stream>>>(
       vis_count, (const uint32_t *)(ws + L.dvals_tmp), depth_order, depth_hist_used, (const uint4 *)tile_span, tg.tiles_x,
       (unsigned long long)max_dup, scan_status, ctr, tkeys_a,
-      tgids_a, blend_rank, tile_hist, info_dev);
+      tgids_a, blend_rank, tile_hist, tile_bits > 16 ? 1 : 0, info_dev);
   GSR_LAUNCH_CHECK();
 
   // 3. stable sort of the pairs by tile id
