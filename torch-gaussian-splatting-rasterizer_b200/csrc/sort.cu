@@ -331,9 +331,21 @@ static int pick_items(int64_t n, int sms) {
 }
 // Look-back status words: one row of 256 per tile and pass, for the tile size the launcher will pick for this n on the
 // current device (both are known on the host), so the per-frame memset covers kilobytes, not megabytes.
+// GSR_SORT_REST_ITEMS=4..24: tile size of the passes AFTER a filtering first pass (they see only the survivors, so a
+// smaller tile spreads them over more SMs); 0 / unset: the same tile as the first pass.  Experiment knob.
+static int rest_items_cap() {
+  static const int v = [] {
+    const char *e = getenv("GSR_SORT_REST_ITEMS");
+    const int c = e ? atoi(e) : 0;
+    return (c < 4 || c > 24) ? 0 : (c / 4) * 4;
+  }();
+  return v;
+}
 static int64_t sort_tiles(int64_t n) {
   const int64_t n1 = n > 0 ? n : 1;
-  return ceil_div64(n1, (int64_t)kBigThreads * pick_items(n1, sm_count()));
+  int items = pick_items(n1, sm_count());
+  if (rest_items_cap() && rest_items_cap() < items) items = rest_items_cap();
+  return ceil_div64(n1, (int64_t)kBigThreads * items);
 }
 
 size_t sort_scratch_bytes(int64_t n) {
@@ -369,8 +381,8 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
   const int passes = (bits + 7) / 8;
   const int last_bits = bits - 8 * (passes - 1);
   const uint32_t last_mask = (1u << last_bits) - 1u;
-  const int items = pick_items(n, sm_count());
-  const int64_t tiles = ceil_div64(n, (int64_t)kBigThreads * items);
+  const int items0 = pick_items(n, sm_count());
+  const int items_rest = (live_flags && rest_items_cap() && rest_items_cap() < items0) ? rest_items_cap() : items0;
   const size_t zero_bytes = sizeof(uint32_t) * (kMaxPasses * kRadix + 8 + (size_t)passes * s.status_stride);
   if (!scratch_zeroed) GSR_CHECK_CUDA(cudaMemsetAsync(s.hist, 0, zero_bytes, stream));
   const uint32_t *hist = ready_hist ? ready_hist : s.hist;  // digit counts may come from the producer of the keys
@@ -390,6 +402,8 @@ int launch_sort_pairs(const uint32_t *keys_in, const uint32_t *values_in, uint32
     uint32_t *vout = to_out ? values_out : values_tmp;
     if (p == passes - 1 && skip_final_keys && !adaptive) kout = nullptr;  // caller only wants the permutation
     const uint32_t mask = (p == passes - 1) ? last_mask : 255u;
+    const int items = p == 0 ? items0 : items_rest;
+    const int64_t tiles = ceil_div64(n, (int64_t)kBigThreads * items);
     const size_t smem = sizeof(uint32_t) * 2 * (size_t)kBigThreads * items;
     const bool filter = p == 0 && live_flags != nullptr;
     const uint32_t *hist_p = hist + p * kRadix;
