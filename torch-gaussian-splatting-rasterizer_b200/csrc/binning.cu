@@ -23,7 +23,10 @@
 namespace gsr {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
+#ifndef GSR_SCAN_ITEMS
+#define GSR_SCAN_ITEMS 4
+#endif
+constexpr int kScanItems = GSR_SCAN_ITEMS;  // Gaussians per thread (slot = lane * kScanItems + j must fit 7 bits)
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kStageCap = 1024;  // pairs a warp can stage in shared memory (one word each)
 constexpr int kStageWords = kStageCap + 32 * kScanItems + (32 * kScanItems + 1) + 3;  // + ids + offsets, 16-byte multiple
