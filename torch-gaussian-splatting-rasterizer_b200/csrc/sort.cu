@@ -40,13 +40,46 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
 __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool live = true) {
   uint32_t peers = __ballot_sync(0xFFFFFFFFu, live);
   peers = live ? peers : ~peers;
+  // Four instructions per bit (test into a predicate, vote, mask from the predicate, one LOP3: peers & ~(vote ^ mask)).
+  // Written as PTX because the C form compiles to six (a shift and a second compare per bit) and these passes are bound
+  // by the integer pipe.
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
-    const bool bit = (d >> b) & 1u;
-    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, bit);
-    peers &= bit ? vote : ~vote;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v, m;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+        "selp.b32 m, 0xffffffff, 0, p;\n\t"
+        "lop3.b32 %0, %0, v, m, 0x90;\n\t"
+        "}"
+        : "+r"(peers)
+        : "r"(d), "r"(1u << b));
   }
   return peers;
+}
+
+// Shared memory through 32-bit addresses computed once per thread.  Indexing the __shared__ arrays directly made the
+// compiler rebuild the shared-window base (S2R CgaCtaId, LEA ...) at every use inside the unrolled per-key loops - ten
+// integer instructions per key in kernels that are bound by the integer pipe.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ---- digit histograms of all passes, one read of the keys --------------------------------------------------
@@ -176,31 +209,46 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
   }
 
-  // ---- load: warp w owns the contiguous run [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item i of lane l at i*32+l ----
-  const int64_t base = (int64_t)tile * TILE + warp * (ITEMS * 32) + lane;
+  // ---- load: warp w owns the contiguous run [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item i of lane l at i*32+l.
+  //      Indices are 32-bit: n < 2^30 and tile * TILE < n + TILE ----
+  static_assert(ITEMS % 2 == 0, "ranks are packed two per register");
+  const uint32_t base = tile * (uint32_t)TILE + (uint32_t)(warp * (ITEMS * 32) + lane);
+  const int32_t left = (int32_t)(uint32_t)n - (int32_t)base;  // item i exists iff i * 32 < left
+  const uint32_t *kp = keys_in + base;
   uint32_t key[ITEMS];
   uint32_t live_mask = 0xFFFFFFFFu;  // FILTER: bit i = item i takes part
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const int64_t idx = base + i * 32;
-    key[i] = idx < n ? __ldg(keys_in + idx) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
-    if (FILTER && !(idx < n && (__ldg(live_flags + idx) >> 31))) live_mask &= ~(1u << i);
+    const bool in = i * 32 < left;
+    key[i] = in ? __ldg(kp + i * 32) : 0xFFFFFFFFu;  // sentinels carry the largest digit and come last
+    if (FILTER && !(in && (__ldg(live_flags + base + i * 32) >> 31))) live_mask &= ~(1u << i);
   }
 
-  // ---- rank inside the warp, in (item, lane) order ----
-  uint16_t rank[ITEMS];
+  // ---- rank inside the warp, in (item, lane) order.  The highest lane of a group of equal digits leads it (one FLO);
+  //      ranks are packed two per register and pinned there (left alone, the compiler kept the vote masks instead and
+  //      redid the popcounts in the scatter phase: 48 live registers, spills) ----
+  const uint32_t hist_row = smem_addr(&s_hist[warp][0]);
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  uint32_t rank2[ITEMS / 2];
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
     const bool live = !FILTER || ((live_mask >> i) & 1u);
     const uint32_t peers = FILTER ? match_digit(d, live) : match_digit(d);
-    const int leader = __ffs(peers) - 1;
+    const int leader = 31 - __clz(peers);
+    const bool lead = lane == leader && live;
+    const uint32_t slot = hist_row + 2u * d;
     uint32_t before = 0;
-    if (lane == leader && live) before = s_hist[warp][d];
+    if (lead) before = lds_u16(slot);
     before = __shfl_sync(0xFFFFFFFFu, before, leader);
-    rank[i] = (uint16_t)(before + __popc(peers & ((1u << lane) - 1u)));
-    if (lane == leader && live) s_hist[warp][d] = (uint16_t)(before + __popc(peers));
+    const uint32_t r = before + __popc(peers & lanes_below);
+    if (lead) sts_u16(slot, before + __popc(peers));
     __syncwarp();
+    if (i & 1)
+      rank2[i / 2] |= r << 16;
+    else
+      rank2[i / 2] = r;
+    asm volatile("" : "+r"(rank2[i / 2]));
   }
   __syncthreads();
 
@@ -282,33 +330,39 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   // ---- scatter to the tile-local sorted position.  Keys first (their registers are then free), then all value loads
   //      of the thread are issued back to back before the first one is stored: in a fused loop every shared-memory
   //      store waited for its own global load (a quarter of the kernel's stall samples) ----
+  const uint32_t excl_base = smem_addr(s_excl), keys_base = smem_addr(s_keys), vals_base = smem_addr(s_vals);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
-    const uint32_t pos = s_excl[d] + s_hist[warp][d] + rank[i];
-    if (!FILTER || ((live_mask >> i) & 1u)) s_keys[pos] = key[i];
-    rank[i] = (uint16_t)pos;  // TILE <= 24576 fits
+    const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
+    const uint32_t pos = lds_u32(excl_base + 4u * d) + lds_u16(hist_row + 2u * d) + r;  // < TILE <= 24576
+    if (!FILTER || ((live_mask >> i) & 1u)) sts_u32(keys_base + 4u * pos, key[i]);
+    if (i & 1)
+      rank2[i / 2] = (rank2[i / 2] & 0xFFFFu) | (pos << 16);
+    else
+      rank2[i / 2] = (rank2[i / 2] & 0xFFFF0000u) | pos;
   }
   {
     uint32_t val[ITEMS];
+    const uint32_t *vp = vals_in ? vals_in + base : nullptr;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) val[i] = i * 32 < left ? (vp ? __ldg(vp + i * 32) : base + i * 32) : 0u;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      const int64_t idx = base + i * 32;
-      val[i] = idx < n ? (vals_in ? __ldg(vals_in + idx) : (uint32_t)idx) : 0u;
+      const uint32_t pos = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
+      if (!FILTER || ((live_mask >> i) & 1u)) sts_u32(vals_base + 4u * pos, val[i]);
     }
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i)
-      if (!FILTER || ((live_mask >> i) & 1u)) s_vals[rank[i]] = val[i];
   }
   __syncthreads();
   // ---- runs of equal digits leave coalesced ----
   const int64_t remaining = n - (int64_t)tile * TILE;
   const int valid = FILTER ? (int)s_live_total : (remaining < TILE ? (int)remaining : TILE);
+  const uint32_t gbase_base = smem_addr(s_gbase);
   for (int j = tid; j < valid; j += kBigThreads) {
-    const uint32_t k = s_keys[j];
-    const uint32_t dst = s_gbase[(k >> shift) & mask] + j;
+    const uint32_t k = lds_u32(keys_base + 4u * j);
+    const uint32_t dst = lds_u32(gbase_base + 4u * ((k >> shift) & mask)) + j;
     if (keys_out) keys_out[dst] = k;
-    vals_out[dst] = s_vals[j];
+    vals_out[dst] = lds_u32(vals_base + 4u * j);
   }
 }
 
