@@ -35,6 +35,9 @@
 #ifndef GSR_BLEND_GROUP
 #define GSR_BLEND_GROUP 4   // records walked per warp vote (unrolled); 2 halves the loop body (A/B builds)
 #endif
+#ifndef GSR_BLEND_PIN
+#define GSR_BLEND_PIN 1     // pin the pixel column and the running record address in registers (A/B builds: 0)
+#endif
 #ifndef GSR_DEFAULT_BLEND_STAGE
 #define GSR_DEFAULT_BLEND_STAGE 2   // kStageWarp: measured fastest (profiles/r02_blend_variants_C3.json)
 #endif
@@ -89,7 +92,10 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   const int px = tile_x * GSR_TILE + warp * COLS + (lane % COLS);
   const int py0 = tile_y * GSR_TILE + (lane / COLS);
   const uint2 range = ranges[tile_y * tiles_x + tile_x];
-  const float fx = (float)px;
+  float fx = (float)px;
+#if GSR_BLEND_PIN
+  asm volatile("" : "+f"(fx));  // keep it in its register: under the 56-register cap the compiler redid the I2F per group
+#endif
 
   // A terminated (or unwritable) pixel is parked at y = 1e18: it fails the power test like any other miss, and "all
   // my pixels are parked" is read off fy itself - no live counter to maintain in the blend path.
@@ -190,9 +196,10 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       if (T[k] < kStopT) fy[k] = kParkedY;
     }
   };
-  auto powers = [&](const float *r, float power[PX], float &thr) -> bool {
-    const float4 q = *reinterpret_cast<const float4 *>(r);      // mx my A C
-    const float2 w = *reinterpret_cast<const float2 *>(r + 4);  // B thr
+  auto powers = [&](uint32_t r, float power[PX], float &thr, float2 &orr) -> bool {
+    const float4 q = lds_f4(r);       // mx my A C
+    const float4 w = lds_f4(r + 16);  // B thr opacity red
+    orr = make_float2(w.z, w.w);
     const float dx = fsub(q.x, fx);
     const float adx2 = fmul(q.z, fmul(dx, dx));
     const float bdx = fmul(w.x, dx);
@@ -218,6 +225,9 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
   };
   // walk one staged batch; returns when the batch is consumed or the whole warp has terminated
   auto eval_batch = [&](const float *base, int count, uint32_t list_base) {
+    // Records are read through a 32-bit shared address that advances with the loop (ld.shared in blend_common.cuh):
+    // indexing s_rec made the compiler rebuild the address from S2R CgaCtaId / TID.X at the head of every group.
+    uint32_t group = smem_addr32(base);
     // The list is walked four records at a time with no bound check inside the group: slots past the end of the
     // list hold thr = +inf (see `issue`), so they fail the test like any other miss.
     const int count4 = (count + (GSR_BLEND_GROUP - 1)) & ~(GSR_BLEND_GROUP - 1);
@@ -233,11 +243,11 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       }
 #pragma unroll
       for (int u = 0; u < GSR_BLEND_GROUP; ++u) {
-        const float *r = base + (j + u) * GSR_REC_FLOATS;
+        const uint32_t r = group + u * (GSR_REC_FLOATS * (uint32_t)sizeof(float));
         float power[PX], thr;
-        if (powers(r, power, thr)) {
-          const float2 orr = *reinterpret_cast<const float2 *>(r + 6);  // opacity r
-          const float4 gbl = *reinterpret_cast<const float4 *>(r + 8);  // g b log2(opacity) .
+        float2 orr;  // opacity r
+        if (powers(r, power, thr, orr)) {
+          const float4 gbl = lds_f4(r + 32);  // g b log2(opacity) .
           float pmax = power[0];
 #pragma unroll
           for (int k = 1; k < PX; ++k) pmax = fmaxf(pmax, power[k]);
@@ -256,6 +266,10 @@ blend_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gids, 
       // the warp is converged: a `break` inside the divergent slow path makes the compiler postpone reconvergence
       // to the loop exit, after which lanes run the loop one by one (measured: 1.5 active lanes per instruction).
       if (!__any_sync(0xFFFFFFFFu, alive())) break;
+      group += GSR_BLEND_GROUP * (GSR_REC_FLOATS * (uint32_t)sizeof(float));
+#if GSR_BLEND_PIN
+      asm volatile("" : "+r"(group));
+#endif
     }
   };
 

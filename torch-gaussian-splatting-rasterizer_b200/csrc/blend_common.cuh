@@ -137,6 +137,12 @@ __device__ __forceinline__ void blend_power4(float my, float C, float adx2, floa
 }
 
 // cp.async (LDGSTS) staging helpers shared by the forward and backward blend kernels
+__device__ __forceinline__ uint32_t smem_addr32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {  // after cp_async_wait / mbar_wait (volatile asm keeps the order)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
