@@ -177,13 +177,23 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
         const uint32_t slot = (uint32_t)(lane * kScanItems + j);
         const uint32_t origin = r.y0 * (uint32_t)tiles_x + r.x0;
         if (r.area <= (uint32_t)kCullMaxTiles) {
-          unsigned long long m = r.mask;
-          const uint32_t inv = (65536u + r.w - 1u) / r.w;  // exact row = bit / w for bit < 64
-          while (m) {
-            const uint32_t bit = (uint32_t)__ffsll((long long)m) - 1u;
-            m &= m - 1;
+          // row = bit / w through a reciprocal: any inv in [65536/w, 65536/w + 2) gives the exact quotient for
+          // bit < 64, w <= 64 (the excess bit*(inv - 65536/w)/65536 < 1/64 never carries), and the approximate
+          // division is within 0.016 of 65536/w, whose fraction is 0 or >= 1/64 - so trunc + 1 lands in that interval.
+          // The mask is walked as two 32-bit halves (64-bit ffs / clear-lowest cost 25 instructions per pair).
+          const uint32_t inv = __float2uint_rz(__fdividef(65536.0f, (float)r.w)) + 1u;
+          auto put = [&](uint32_t bit) {
             const uint32_t row = (bit * inv) >> 16, col = bit - row * r.w;
             stage[off++] = ((origin + row * (uint32_t)tiles_x + col) << 7) | slot;
+          };
+          uint32_t lo = (uint32_t)r.mask, hi = (uint32_t)(r.mask >> 32);
+          while (lo) {
+            put((uint32_t)__ffs((int)lo) - 1u);
+            lo &= lo - 1u;
+          }
+          while (hi) {
+            put((uint32_t)__ffs((int)hi) + 31u);
+            hi &= hi - 1u;
           }
         } else {
           for (uint32_t ty = 0; ty < r.h; ++ty)
@@ -243,16 +253,16 @@ scan_emit_kernel(const uint32_t *__restrict__ n_dev, const uint32_t *__restrict_
   __syncthreads();  // s_base is known; every warp's staging buffer (written by its own lanes) is complete
   const unsigned long long warp_out = s_base + warp_rel;
   if (staged) {
-    for (uint32_t e = lane; e < (uint32_t)warp_total; e += 32) {
-      const unsigned long long out = warp_out + e;
-      if (out < capacity) {
-        const uint32_t pr = stage[e], tile_id = pr >> 7;
-        tile_keys[out] = tile_id;
-        tile_gids[out] = s_gid[pr & 127u];
-        atomicAdd(&s_hist[0][tile_id & 255u], 1u);
-        atomicAdd(&s_hist[1][(tile_id >> 8) & 255u], 1u);
-        if (wide_tiles) atomicAdd(&s_hist[2][tile_id >> 16], 1u);  // third pass: frames above 65536 tiles (uniform branch)
-      }
+    const unsigned long long room = capacity > warp_out ? capacity - warp_out : 0ull;  // pairs beyond it are dropped
+    const uint32_t limit = (uint32_t)(warp_total < room ? warp_total : room);          // warp-uniform, <= kStageCap
+    uint32_t *keys_out = tile_keys + warp_out, *gids_out = tile_gids + warp_out;
+    for (uint32_t e = lane; e < limit; e += 32) {
+      const uint32_t pr = stage[e], tile_id = pr >> 7;
+      keys_out[e] = tile_id;
+      gids_out[e] = s_gid[pr & 127u];
+      atomicAdd(&s_hist[0][tile_id & 255u], 1u);
+      atomicAdd(&s_hist[1][(tile_id >> 8) & 255u], 1u);
+      if (wide_tiles) atomicAdd(&s_hist[2][tile_id >> 16], 1u);  // third pass: frames above 65536 tiles (uniform branch)
     }
   } else if (warp_total != 0) {
     // ---- fallback for a warp with more pairs than the staging buffer holds ----
