@@ -180,8 +180,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   extern __shared__ uint32_t s_dyn[];                      // s_keys[TILE] | s_vals[TILE]
   uint32_t *s_keys = s_dyn, *s_vals = s_dyn + TILE;
   __shared__ uint16_t s_hist[kBigWarps][kRadix];           // per-warp digit counts, then exclusive over warps (< TILE <= 65535)
-  __shared__ uint32_t s_excl[kRadix];                      // first tile-local slot of each digit
-  __shared__ uint32_t s_gbase[kRadix];                     // global slot of a digit's first pair minus s_excl
+  __shared__ uint32_t s_gbase[kRadix];                     // global slot of a digit's first pair minus its tile-local slot
   __shared__ uint2 s_scan[kRadix / 32];
   __shared__ uint32_t s_part[4][kRadix];
   __shared__ uint32_t s_open[kRadix];
@@ -252,17 +251,26 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
   __syncthreads();
 
-  // ---- thread d (< 256) owns digit d: counts over warps -> exclusive, tile count ----
+  // ---- thread d (< 256) owns digit d: tile count, scan over the digits, then each warp's count is replaced by the
+  //      tile-local slot of its first key of that digit (digit offset folded in: one shared load per key in the scatter
+  //      phase instead of two - these passes queue on the shared-memory pipe) ----
   uint32_t count = 0;
   if (tid < kRadix) {
 #pragma unroll 8
-    for (int w = 0; w < kBigWarps; ++w) {
-      const uint32_t c = s_hist[w][tid];
-      s_hist[w][tid] = (uint16_t)count;
-      count += c;
-    }
+    for (int w = 0; w < kBigWarps; ++w) count += s_hist[w][tid];
+    // published at once: successors look back for it while this CTA is still scanning
+    st_volatile_u32(status + (size_t)tile * kRadix + tid, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
   }
   const uint2 ex = block_exclusive_scan2(make_uint2(count, tid < kRadix ? __ldg(hist + tid) : 0u), s_scan);
+  if (tid < kRadix) {
+    uint32_t run = ex.x;
+#pragma unroll 8
+    for (int w = 0; w < kBigWarps; ++w) {
+      const uint32_t c = s_hist[w][tid];
+      s_hist[w][tid] = (uint16_t)run;  // < TILE <= 24576
+      run += c;
+    }
+  }
   if (FILTER && tid == kRadix - 1) {
     s_live_total = ex.x + count;                                      // survivors of this tile
     if (tile == 0) *n_out = ex.y + __ldg(hist + tid);                 // survivors of the whole input
@@ -275,8 +283,6 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     const int d = tid & (kRadix - 1), quarter = tid >> 8;
     uint32_t *my_status = status + (size_t)tile * kRadix + d;
     if (quarter == 0) {
-      s_excl[d] = ex.x;
-      st_volatile_u32(my_status, (tile == 0 ? kFlagInclusive : kFlagAggregate) | count);
       s_open[d] = tile != 0;
     }
     uint32_t prefix = 0;
@@ -330,12 +336,12 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   // ---- scatter to the tile-local sorted position.  Keys first (their registers are then free), then all value loads
   //      of the thread are issued back to back before the first one is stored: in a fused loop every shared-memory
   //      store waited for its own global load (a quarter of the kernel's stall samples) ----
-  const uint32_t excl_base = smem_addr(s_excl), keys_base = smem_addr(s_keys), vals_base = smem_addr(s_vals);
+  const uint32_t keys_base = smem_addr(s_keys), vals_base = smem_addr(s_vals);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const uint32_t d = (key[i] >> shift) & mask;
     const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xFFFFu);
-    const uint32_t pos = lds_u32(excl_base + 4u * d) + lds_u16(hist_row + 2u * d) + r;  // < TILE <= 24576
+    const uint32_t pos = lds_u16(hist_row + 2u * d) + r;  // < TILE <= 24576
     if (!FILTER || ((live_mask >> i) & 1u)) sts_u32(keys_base + 4u * pos, key[i]);
     if (i & 1)
       rank2[i / 2] = (rank2[i / 2] & 0xFFFFu) | (pos << 16);
