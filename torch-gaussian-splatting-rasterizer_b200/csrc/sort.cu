@@ -145,12 +145,21 @@ __device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 *s_warp /*
 }
 
 // ---- one pass -----------------------------------------------------------------------------------------------
-// Big tiles: 1024 threads x ITEMS keys, one CTA per SM, the tile staged in (dynamic) shared memory.  A first version
+// Big tiles: GSR_SORT_THREADS threads x ITEMS keys, the tile staged in (dynamic) shared memory.  A first version
 // with 4096-key tiles spent most of each pass in the look-back: all CTAs of a wave publish their aggregates at about
 // the same time, so CTA t walks back over t unresolved predecessors - ~300 with two small CTAs per SM, wave after
 // wave.  With ITEMS chosen so that the whole sort is one or two waves of at most 148 CTAs the walk is a handful of
 // 32-wide rounds and the number of look-backs drops 5x.
-constexpr int kBigThreads = 1024;
+#ifndef GSR_SORT_THREADS
+// Threads per CTA (tile = threads x ITEMS keys).  1024: one CTA owns the SM's whole register file.  512 (default): two CTAs
+// per SM whose phases (load / rank / look-back / store) overlap, and a sort CTA of one frame can start beside resident
+// blend CTAs of another.  Measured (profiles/r02_notes.md): C3 binning alone 0.249 -> 0.262 ms, but three frames in
+// flight 0.679 -> 0.667 ms per frame, and C5 (20 M pairs, several waves) 0.667 -> 0.605 ms.  256: 0.678 pipelined.
+#define GSR_SORT_THREADS 512
+#endif
+constexpr int kBigThreads = GSR_SORT_THREADS;
+constexpr int kQuarters = kBigThreads / 256;              // groups of 256 threads: one per look-back window
+constexpr int kBigCtasPerSm = 1024 / kBigThreads;
 constexpr int kBigWarps = kBigThreads / 32;
 
 // FILTER: the first pass of a sort whose input still holds entries that must not take part (bit 31 of live_flags[i]
@@ -170,7 +179,7 @@ __device__ __forceinline__ bool pass_is_identity(const uint32_t *__restrict__ hi
 }
 
 template <int ITEMS, bool FILTER>
-__global__ void __launch_bounds__(kBigThreads, 1)
+__global__ void __launch_bounds__(kBigThreads, kBigCtasPerSm)
 onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n_host,
                 const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ hist, uint32_t *status,
@@ -182,7 +191,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   __shared__ uint16_t s_hist[kBigWarps][kRadix];           // per-warp digit counts, then exclusive over warps (< TILE <= 65535)
   __shared__ uint32_t s_gbase[kRadix];                     // global slot of a digit's first pair minus its tile-local slot
   __shared__ uint2 s_scan[kRadix / 32];
-  __shared__ uint32_t s_part[4][kRadix];
+  __shared__ uint32_t s_part[kQuarters][kRadix];
   __shared__ uint32_t s_open[kRadix];
   __shared__ uint32_t s_tile, s_live_total;
 
@@ -315,7 +324,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
       if (quarter == 0 && open) {
         bool done = false;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kQuarters; ++q) {
           if (!done) {
             const uint32_t pq = s_part[q][d];
             prefix += pq & 0x7FFFFFFFu;
@@ -324,7 +333,7 @@ onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         }
         if (done) s_open[d] = 0;
       }
-      prev -= 32;
+      prev -= kQuarters * 8;
     }
     if (quarter == 0) {
       if (tile != 0) st_volatile_u32(my_status, kFlagInclusive | ((prefix + count) & kValueMask));
@@ -385,7 +394,7 @@ static int pick_items(int64_t n, int sms) {
   for (int it : options) {
     if (it > cap) break;
     best = it;
-    if (ceil_div64(n, (int64_t)kBigThreads * it) <= sms) return it;
+    if (ceil_div64(n, (int64_t)kBigThreads * it) <= (int64_t)sms * kBigCtasPerSm) return it;
   }
   return best;
 }
