@@ -70,5 +70,10 @@ if __name__ == "__main__":
     section("prepare_kernel: the view-independent half (FP64 exp, quaternion normalisation), once per model",
             find("14prepare_kernel")[0], pattern=r"STG|DFMA")
     section("onesweep_kernel<24,false>: ballot ranking, look-back", find("onesweep_kernelILi24ELb0E")[0],
-            pattern=r"VOTE|ATOM|LDG|STG|BAR")
+            pattern=r"ATOM|LDG|STG|BAR")
+    rows = sass(find("onesweep_kernelILi24ELb0E")[0])
+    r2p = [i for i, (_, ins) in enumerate(rows) if ins.startswith("R2P")]
+    print("    ... one key of the ranking loop (R2P sets the digit's bits as predicates; per bit VOTE + SEL + LOP3):")
+    for a, ins in rows[r2p[8]:r2p[9] + 1]:
+        print(f"    {a}  {ins}")
     section("scan_emit_kernel", find("scan_emit_kernel")[0], pattern=r"VOTE|ATOM|LDG|STG|BAR")
