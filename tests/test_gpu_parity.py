@@ -82,7 +82,8 @@ def test_preprocess_matches_reference_and_oracle(name, golden, R):
     assert np.array_equal(from_span[vis], (tt & 0x7FFFFFFF)[vis].astype(np.int64))
 
 
-@pytest.mark.parametrize("n,bits", [(1, 32), (255, 32), (4096, 32), (4097, 32), (100_003, 32), (1_000_000, 32),
+@pytest.mark.parametrize("n,bits", [(1, 32), (255, 32), (2048, 32), (2049, 32), (4096, 32), (4097, 32), (12_289, 32),
+                                    (100_003, 32), (1_000_000, 32), (3_700_001, 32),  # the last one: more than one wave of tiles
                                     (300_000, 13), (50_000, 5), (70_000, 9)])
 def test_radix_sort_is_the_stable_sort(n, bits, R):
     rng = np.random.default_rng(n + bits)
