@@ -44,12 +44,14 @@ struct PreDebug {  // optional outputs of the raw kernel (tests); all null in th
 
 // S6 = upper triangle of Sigma (S00 S01 S02 S11 S12 S22).  `colour(dx, dy, dz, rgb)` evaluates sh_to_rgb for this
 // lane's Gaussian; it is only called for Gaussians that keep at least one tile (or when debug outputs are requested).
-template <bool HIST, typename Colour>
+// `warm()` is called as soon as the Gaussian is known to keep a non-empty rect in this rank's band - the per-view
+// kernel uses it to prefetch the SH rows of survivors only when it renders a band of the frame.
+template <bool HIST, typename Colour, typename Warm>
 __device__ __forceinline__ void pre_body(PreShared &sm, const gsr_camera &cam, const TileGrid &tg, int row_begin,
                                          int row_end, bool active, int64_t i, const float p[3], const float S6[6],
                                          float opacity, float thr, float log2o, uint32_t *__restrict__ depth_key,
                                          uint32_t *__restrict__ tiles_touched, uint4 *__restrict__ span_out,
-                                         float4 *__restrict__ rec, const PreDebug &dbg, Colour colour) {
+                                         float4 *__restrict__ rec, const PreDebug &dbg, Colour colour, Warm warm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ---- A: geometry, rasterize.py:371-420 ----
   float camp[3], clip[4];
@@ -79,6 +81,7 @@ __device__ __forceinline__ void pre_body(PreShared &sm, const gsr_camera &cam, c
   int x0 = min(rr[0], tg.tiles_x_eff), x1 = min(rr[2], tg.tiles_x_eff);
   int y0 = max(min(rr[1], tg.tiles_y_eff), row_begin), y1 = min(min(rr[3], tg.tiles_y_eff), row_end);
   const bool blendable = active && !skip && x1 > x0 && y1 > y0;  // the reference's loop would blend it
+  if (blendable) warm();
 
   // ---- B: drop the (Gaussian, tile) pairs in which no pixel can pass alpha > 1/255 (the image is unchanged) ----
   // B1 (per lane): the pixels that can pass lie in the ellipse power >= limit of the conic THE BLEND KERNEL USES
@@ -272,10 +275,10 @@ preprocess_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
     };
     if (depth_hist)
       pre_body<true>(sm, cam, tg, row_begin, row_end, active, i, p, S6, opacity, thr, log2o, depth_key, tiles_touched,
-                     span_out, rec, dbg, colour);
+                     span_out, rec, dbg, colour, [] {});
     else
       pre_body<false>(sm, cam, tg, row_begin, row_end, active, i, p, S6, opacity, thr, log2o, depth_key, tiles_touched,
-                      span_out, rec, dbg, colour);
+                      span_out, rec, dbg, colour, [] {});
   }
   if (depth_hist) {
     __syncthreads();
@@ -351,7 +354,8 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_CTAS)
 preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__restrict__ shb, int64_t n,
                            const __grid_constant__ gsr_camera cam, int row_begin, int row_end,
                            uint32_t *__restrict__ depth_key, uint32_t *__restrict__ tiles_touched,
-                           uint4 *__restrict__ span_out, float4 *__restrict__ rec, uint32_t *__restrict__ depth_hist) {
+                           uint4 *__restrict__ span_out, float4 *__restrict__ rec, uint32_t *__restrict__ depth_hist,
+                           int late_sh /* prefetch SH rows only for Gaussians that keep a rect (band renders) */) {
   __shared__ PreShared sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < 1024; k += kPreThreads) (&sm.hist[0][0])[k] = 0;
@@ -391,10 +395,12 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
     {  // L2 prefetch: this block's SH rows (wanted ~400 instructions from now, and fetched from DRAM at sector granularity
        // whether or not the neighbours turn out visible) and the next block's geometry rows - no registers held
       const float4 *spf = shb + blk * (kPrepShRows * 32) + lane;
+      if (!late_sh) {
 #pragma unroll
-      for (int r = 0; r < 3 * rows; ++r) {
-        const int c = r / rows, j = r % rows;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(spf + (c * 4 + j) * 32));
+        for (int r = 0; r < 3 * rows; ++r) {
+          const int c = r / rows, j = r % rows;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(spf + (c * 4 + j) * 32));
+        }
       }
 #if GSR_PRE_PREFETCH == 1
       const int64_t nb = blk + (int64_t)gridDim.x * (kPreThreads / 32);
@@ -424,8 +430,19 @@ preprocess_prepared_kernel(const float4 *__restrict__ geom, const float4 *__rest
           return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w));
         });
     };
+    auto warm = [&]() {
+#if GSR_PRE_PREFETCH
+      if (late_sh) {
+#pragma unroll
+        for (int r = 0; r < 3 * rows; ++r) {
+          const int c = r / rows, j = r % rows;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (c * 4 + j) * 32));
+        }
+      }
+#endif
+    };
     pre_body<true>(sm, cam, tg, row_begin, row_end, active, i, p, S6, q0.w, q2.z, q2.w, depth_key, tiles_touched, span_out,
-                   rec, dbg, colour);
+                   rec, dbg, colour, warm);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < 1024; k += kPreThreads) {
@@ -527,10 +544,18 @@ int launch_preprocess_prepared(const void *prepared, int64_t n, const gsr_camera
   }();
   const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
   if (blocks > resident) blocks = resident;
+  // A band render keeps a rect for a fraction of the Gaussians only: their SH rows (192 of the 240 bytes per Gaussian)
+  // are then prefetched once the rect is known instead of up front for everybody.  GSR_PRE_LATE_SH=0/1 forces the mode.
+  static const int late_env = [] {
+    const char *e = getenv("GSR_PRE_LATE_SH");
+    return e ? atoi(e) : -1;
+  }();
+  const TileGrid tgh = make_grid(cam->width, cam->height);
+  const int late_sh = late_env >= 0 ? late_env : ((row_begin > 0 || row_end < tgh.tiles_y_eff) ? 1 : 0);
 #define GSR_PRE(D)                                                                                                  \
   preprocess_prepared_kernel<D><<<blocks, kPreThreads, 0, stream>>>(geom, shb, n, *cam, row_begin, row_end, depth_key, \
                                                                     tiles_touched, (uint4 *)tile_span, (float4 *)rec, \
-                                                                    depth_hist)
+                                                                    depth_hist, late_sh)
   switch (cam->sh_degree) {
     case 0: GSR_PRE(0); break;
     case 1: GSR_PRE(1); break;

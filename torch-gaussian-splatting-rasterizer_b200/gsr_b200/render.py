@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -602,9 +602,10 @@ class Stages:
         self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
         self.image = torch.empty((height, width, 3), dtype=torch.float32, device=dev)
 
-    def preprocess(self, cam: CameraStruct, prepared: bool = True) -> None:
+    def preprocess(self, cam: CameraStruct, prepared: bool = True, rows: Tuple[int, int] = (0, 1 << 30)) -> None:
+        """`rows`: band of tile rows (prepared path), as a rank of a band-sharded render would pass it."""
         if prepared:
-            _cabi.call("gsr_preprocess_prepared_fwd", _cabi.ptr(self.model.prepare()), self.n, ctypes.byref(cam), 0, 1 << 30,
+            _cabi.call("gsr_preprocess_prepared_fwd", _cabi.ptr(self.model.prepare()), self.n, ctypes.byref(cam), rows[0], rows[1],
                        _cabi.ptr(self.depth_key), _cabi.ptr(self.tiles_touched), _cabi.ptr(self.tile_span),
                        _cabi.ptr(self.rec), _cabi.ptr(self.depth_hist), _cabi.stream_handle())
         else:
