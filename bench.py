@@ -652,7 +652,7 @@ def main():
                                      "backward + preprocess / SH backward, gradients of all 59 parameters per Gaussian)"}
         prof = load_profile("r02_kernel_dram.json") or {}
         bl = prof.get("blend_kernel", {})
-        line["roofline"] = {"kernel": "blend_kernel<4,0,0,0,0>", "bound": "fp32_fma", "achieved": blend_tflops, "peak": fp32_peak,
+        line["roofline"] = {"kernel": "blend_kernel<4,0,0,0,2>", "bound": "fp32_fma", "achieved": blend_tflops, "peak": fp32_peak,
                             "unit": "TFLOP/s", "frac": blend_tflops / fp32_peak if fp32_peak else None,
                             "traffic": bl.get("dram_bytes"),
                             "traffic_static": {"static": True, "kernel": bl.get("kernel"), "source": bl.get("source"),
