@@ -213,7 +213,11 @@ class Renderer:
             info = self.frame_info()
             if info["status"] == _cabi.GSR_ERR_DUP_OVERFLOW:  # grow once to the reported need and redo the frame
                 self.clear_status()
+                before = self.max_dup
                 self.reserve(model.n, W, H, max_dup=int(max(info["n_dup"], info["n_dup_peak"]) * 1.1) + 1024)
+                if self.max_dup <= before:  # already at the 2^30 - 1 ceiling of the pair sort: nothing left to grow
+                    raise _cabi.GsrError(info["status"], f"the frame needs {info['n_dup_peak']} (Gaussian, tile) pairs, "
+                                                         f"above the supported capacity {self.max_dup}")
                 continue
             if info["status"] != _cabi.GSR_OK:
                 self.clear_status()
