@@ -98,6 +98,13 @@ def _overflow_worker(rank, world, port):
         # both overflowed: the larger need wins
         r = _FakeRenderer(4, 3000 + 1000 * rank)
         assert gd._agree_on_overflow(r) == int(4000 * 1.1) + 1024
+        # a failure other than an overflow on ONE rank is raised on EVERY rank (nobody is left waiting in a collective)
+        r = _FakeRenderer(3 if rank == 0 else 0, 0)
+        try:
+            gd._agree_on_overflow(r)
+            raise AssertionError("a failed frame on rank 0 went unnoticed on rank %d" % rank)
+        except RuntimeError as exc:
+            assert "status 3" in str(exc) and r.cleared == 1
     finally:
         dist.destroy_process_group()
 

@@ -38,6 +38,23 @@ inline int current_device() {
   cudaGetDevice(&dev);
   return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards: an object bound to
+// a device (gsr_host_renderer) may be driven by a thread whose current device is another one, and a library call must not
+// leave the caller - torch included, which reads cudaGetDevice - on a different device than it came in with.
+struct DeviceScope {
+  int before = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceScope(int device) {
+    status = cudaGetDevice(&before);
+    if (status == cudaSuccess && before != device) status = cudaSetDevice(device);
+    else before = -1;  // nothing to restore
+  }
+  ~DeviceScope() {
+    if (before >= 0) cudaSetDevice(before);
+  }
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+};
 inline int sm_count() {  // SM count of the CURRENT device
   static std::atomic<int> cache[kMaxDevices];
   const int dev = current_device();

@@ -123,7 +123,7 @@ extern "C" int gsr_host_renderer_create(int64_t n_max, int32_t width, int32_t he
 
 extern "C" int gsr_host_renderer_destroy(gsr_host_renderer *h) {
   if (!h) return GSR_OK;
-  cudaSetDevice(h->device);
+  DeviceScope scope(h->device);
   cudaDeviceSynchronize();
   host_renderer_free(h);
   return GSR_OK;
@@ -141,7 +141,8 @@ extern "C" int gsr_host_renderer_submit(gsr_host_renderer *h, const gsr_gaussian
   GSR_REQUIRE(n >= 0 && n <= h->n_max, "n exceeds the renderer's capacity");
   GSR_REQUIRE(cam->width == h->width && cam->height == h->height, "camera image size differs from the renderer's");
   GSR_REQUIRE(n == 0 || (gh->xyz && gh->log_scales && gh->rots && gh->opacity_logit && gh->sh), "null attribute pointer");
-  GSR_CHECK_CUDA(cudaSetDevice(h->device));
+  DeviceScope scope(h->device);  // the caller's current device is restored on every return path
+  GSR_CHECK_CUDA(scope.status);
   const int32_t t = h->next_ticket;
   HostSlot &sl = h->slot[t % h->depth];
   // the frame that used this slot `depth` submissions ago must have been waited for: recycling it silently would lose
@@ -224,7 +225,8 @@ extern "C" int gsr_host_renderer_wait(gsr_host_renderer *h, int32_t ticket, gsr_
   GSR_REQUIRE(ticket >= 0 && ticket < h->next_ticket && ticket >= h->next_ticket - h->depth, "unknown or recycled ticket");
   HostSlot &sl = h->slot[ticket % h->depth];
   GSR_REQUIRE(sl.ticket == ticket, "ticket already recycled");
-  GSR_CHECK_CUDA(cudaSetDevice(h->device));
+  DeviceScope scope(h->device);
+  GSR_CHECK_CUDA(scope.status);
   GSR_CHECK_CUDA(cudaEventSynchronize(sl.done));
   sl.busy = false;
   if (info_host) *info_host = *sl.h_info;

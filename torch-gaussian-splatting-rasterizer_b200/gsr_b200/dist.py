@@ -234,14 +234,16 @@ def _agree_on_overflow(renderer) -> int:
     """Sticky device status of this rank's frames, agreed across the ranks: 0 when every frame of every rank fit its
     pair capacity, else the capacity (max over ranks of the worst frame's need, +10 %) everybody must redraw with."""
     info = renderer.frame_info()
-    need = info["n_dup_peak"] if info["status"] != 0 else 0
-    if info["status"] not in (0, 4):
-        renderer.clear_status()
-        raise RuntimeError(f"libgsr_b200 frame status {info['status']}")
-    if _world()[1] > 1:
-        t = torch.tensor([need], dtype=torch.int64, device=renderer.device if dist.get_backend() == "nccl" else "cpu")
+    need = info["n_dup_peak"] if info["status"] == 4 else 0     # 4 = GSR_ERR_DUP_OVERFLOW
+    failed = info["status"] if info["status"] not in (0, 4) else 0
+    if _world()[1] > 1:  # one MAX all-reduce of two words; every rank takes the same branch below (no rank left waiting)
+        t = torch.tensor([need, failed], dtype=torch.int64,
+                         device=renderer.device if dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        need = int(t.item())
+        need, failed = int(t[0].item()), int(t[1].item())
+    if failed:
+        renderer.clear_status()
+        raise RuntimeError(f"libgsr_b200 frame status {failed} on this or another rank")
     if need:
         renderer.clear_status()
         return int(need * 1.1) + 1024
