@@ -460,6 +460,22 @@ def test_one_process_two_devices(R):
             model = R.GaussianModel.from_cloud(cloud, device=f"cuda:{dev}")
             imgs.append(R.Renderer(device=f"cuda:{dev}").render(model, cam).cpu())
     assert torch.equal(imgs[0], imgs[1])
+    # a host-buffer pipeline bound to cuda:1, driven while cuda:0 is current: same image, and the caller (torch reads
+    # cudaGetDevice) is still on cuda:0 after every call
+    small = cloud.subset(np.arange(20_000))
+    host = [torch.from_numpy(a) for a in (small.xyz, small.scales, small.rots, small.opacity)]
+    sh = torch.from_numpy(small.sh_planar()).permute(2, 1, 0)
+    want = R.Renderer(device="cuda:0").render(R.GaussianModel.from_cloud(small, device="cuda:0"), cam).cpu()
+    with torch.cuda.device(1):
+        hr = R.HostRenderer(small.n, cam.width, cam.height, depth=1, device="cuda:1")
+    torch.cuda.set_device(0)
+    out = torch.empty((cam.height, cam.width, 3)).pin_memory()
+    ticket = hr.submit(*host, sh, cam, out)
+    assert torch.cuda.current_device() == 0
+    hr.wait(ticket)
+    assert torch.cuda.current_device() == 0
+    hr.close()
+    assert torch.cuda.current_device() == 0 and torch.equal(out, want)
 
 
 def test_rasterize_gaussian_loop_matches_reference(golden):
