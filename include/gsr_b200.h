@@ -13,6 +13,9 @@
  *  - all data pointers are DEVICE pointers unless the name ends in _host; the caller owns every
  *    buffer (inputs, outputs, workspace).  Nothing is allocated and nothing synchronises inside the
  *    device entry points: work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - thread safety: the device entry points keep no state between calls (device-specific caches are per device and
+ *    race-free), so different host threads may enqueue frames at the same time as long as each uses its own workspace,
+ *    outputs and stream (tests/test_gpu_guards.py: two threads, two streams).  They act on the CURRENT device.
  *  - float tensors are f32; strides are in ELEMENTS, so any torch view can be passed without a copy.
  *  - Gaussian parameters are the raw 3DGS PLY values: log-scales, un-normalised quaternions (w,x,y,z),
  *    opacity logits, SH coefficients indexed [n, k(16), c(3)].
@@ -162,7 +165,8 @@ int gsr_render_host(const gsr_gaussians *g_host, const gsr_camera *cam, int64_t 
  * until wait(ticket) returns.  At most `depth` tickets may be outstanding: submit() refuses (GSR_ERR_INVALID_ARGUMENT)
  * when the slot it would reuse has not been waited for - nothing is recycled silently, every frame's status is read.
  * wait() returns GSR_ERR_DUP_OVERFLOW (image invalid) when the frame needed more than max_dup pairs; info_host (may be
- * NULL) receives the frame's counters.  render() = submit + wait.  Not thread-safe per object. */
+ * NULL) receives the frame's counters.  render() = submit + wait.  Not thread-safe per object.  The object is bound to the
+ * device that was current in create(); its other calls may be made with any device current and leave it unchanged. */
 typedef struct gsr_host_renderer gsr_host_renderer;
 int gsr_host_renderer_create(int64_t n_max, int32_t width, int32_t height, int64_t max_dup, int32_t depth,
                              gsr_host_renderer **out);

@@ -159,3 +159,59 @@ def test_backward_stays_inside_its_buffers_and_writes_every_gradient(scene, pois
         # sums of float atomics: equal to rounding, never to a poison-sized difference
         scale = float(b[k].abs().max()) + 1e-20
         assert float((a[k] - b[k]).abs().max()) <= 1e-4 * scale, f"{k} depends on stale memory"
+
+
+def test_two_host_threads_render_concurrently(scene):
+    """entry points are stream-ordered and thread-safe per stream.  Two host threads (ctypes drops the GIL
+    around every foreign call), each with its own renderer and stream, enqueue frames of different views at the same
+    time; every frame must equal the one rendered alone.  The error string is per thread."""
+    import threading
+
+    from gsr_b200 import _cabi, render as R
+
+    cloud, cams, model, want, max_dup = scene
+    model.prepare()
+    torch.cuda.synchronize()
+    errors, barrier = [], threading.Barrier(2)
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            r = R.Renderer()
+            barrier.wait()
+            with torch.cuda.stream(stream):
+                for it in range(12):
+                    img = r.render(model, cams[k], check=(it % 4 == 3), prepared=(it % 2 == 0))
+                    if it % 4 == 3 and not torch.equal(img, want[k]):
+                        errors.append(f"thread {k}, frame {it}: image differs from the frame rendered alone")
+            # a failing call in each thread, with different messages: after BOTH have failed, each thread still reads its own
+            expect = ("bad arguments", "depth must be 1..4")[k]
+            barrier.wait()
+            try:
+                if k == 0:
+                    _cabi.call("gsr_render_workspace_bytes", N, -1, H, max_dup, ctypes.byref(ctypes.c_size_t()))
+                else:
+                    _cabi.call("gsr_host_renderer_create", 0, 8, 8, 8, 9, ctypes.byref(ctypes.c_void_p()))
+                errors.append(f"thread {k}: invalid arguments accepted")
+            except _cabi.GsrError as exc:
+                if expect not in str(exc):
+                    errors.append(f"thread {k}: unexpected error string {exc}")
+            barrier.wait()
+            again = _cabi.load().gsr_last_error().decode()
+            if expect not in again:
+                errors.append(f"thread {k}: gsr_last_error() is not per thread: {again!r}")
+            stream.synchronize()
+        except Exception as exc:  # noqa: BLE001 - reported by the main thread
+            errors.append(f"thread {k}: {exc!r}")
+            try:
+                barrier.abort()
+            except Exception:  # noqa: BLE001
+                pass
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
