@@ -231,8 +231,11 @@ blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gi
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef GSR_PREBWD_CTAS
+#define GSR_PREBWD_CTAS 1   // resident CTAs per SM the kernel is compiled for (A/B builds; see profiles/r02_notes.md)
+#endif
 template <int DEGREE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GSR_PREBWD_CTAS)
 preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera cam,
                       const uint32_t *__restrict__ tiles_touched, const float *__restrict__ grad_rec,
                       float *__restrict__ d_xyz, float *__restrict__ d_scales, float *__restrict__ d_rots,
