@@ -231,6 +231,9 @@ blend_bwd_kernel(const float4 *__restrict__ rec, const uint32_t *__restrict__ gi
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef GSR_PREBWD_PREFETCH
+#define GSR_PREBWD_PREFETCH 0   // L2 prefetch of the SH coefficients at the top of preprocess_bwd_kernel (A/B builds)
+#endif
 #ifndef GSR_PREBWD_CTAS
 #define GSR_PREBWD_CTAS 1   // resident CTAs per SM the kernel is compiled for (A/B builds; see profiles/r02_notes.md)
 #endif
@@ -245,6 +248,19 @@ preprocess_bwd_kernel(const gsr_gaussians g, const __grid_constant__ gsr_camera 
   if (i >= g.n) return;
   constexpr int degree = DEGREE;  // compile-time: the basis tables below stay in registers
   constexpr int ncoef = (degree + 1) * (degree + 1);
+#if GSR_PREBWD_PREFETCH
+  // L2 prefetch of this Gaussian's SH coefficients (the planar block: one 128-byte line per coefficient and warp).  They
+  // are wanted a few hundred instructions from now, after the tiles_touched / parameter round trip; the kernel waits on
+  // `long_scoreboard` at 2 CTAs/SM (profiles/r02_backward_ncu.txt) and prefetches hold no registers.  Issued for every
+  // Gaussian: DRAM delivers 32-byte sectors (8 neighbours), so skipping the untouched ones would save nothing.
+  if (g.sh_sn == 1) {
+    const float *spf = g.sh + i;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < ncoef; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(spf + c * g.sh_sc + k * g.sh_sk));
+  }
+#endif
   float gp[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gop = 0.f;
   const bool touched = (__ldg(tiles_touched + i) & 0x7FFFFFFFu) != 0;  // blended somewhere: everything else gets zeros
   float *dsh = d_sh + i * dsh_sn;
