@@ -59,6 +59,31 @@ def test_gaussian_covering_the_whole_frame_takes_the_unculled_large_rect_path():
     assert img.max() > 0.5
 
 
+def test_long_thin_splats_lose_no_pixel_to_the_tile_culling():
+    """for needle-like splats lying diagonally det = c00 c11 - c01^2 cancels in f32 (here by 5-6 digits), so the
+    ellipse of the ROUNDED conic - the one the reference's blend evaluates - differs measurably from the covariance's.
+    The exact tile culling must follow the rounded conic (or keep the whole rect): one lost pixel of a front splat
+    is worth > 1e-3 in the image, and the image is compared at 2e-4.  Few splats, so transmittance stays high."""
+    rng = np.random.default_rng(123)
+    n = 240
+    xyz = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    scales = np.tile(np.log(np.array([1.5, 0.002, 0.002], np.float32)), (n, 1))
+    scales[n // 2:, 0] = np.log(0.4)                      # a shorter kind: rects under the 64-tile mask limit too
+    rots = rng.normal(size=(n, 4)).astype(np.float32)     # every orientation, most of them diagonal on screen
+    z = lambda *s: np.zeros(s, np.float32)
+    f_dc = rng.uniform(0.5, 1.7, (n, 3)).astype(np.float32)
+    cloud = scenes.GaussianCloud(xyz, f_dc, z(n, 45), np.full(n, 2.0, np.float32), scales.astype(np.float32), rots)
+    for w, h in ((640, 400), (333, 217)):
+        cam = camera.camera_for(scenes.Intrinsics.synthetic(w, h), scenes.front_view(0), 3)
+        img, ref, r = _render_both(cloud, cam)
+        c2 = ref["cov2d"].reshape(-1, 4).astype(np.float64)
+        cancel = (c2[:, 0] * c2[:, 3]) / np.maximum(np.abs(c2[:, 0] * c2[:, 3] - c2[:, 1] * c2[:, 2]), 1e-30)
+        assert (cancel > 1e3).sum() > 20                  # the scenario is really there: det cancels by > 3 digits
+        assert img.max() > 0.3
+        assert np.abs(img - ref["image"]).max() < 2e-4
+        assert r.frame_info()["n_visible"] == int((ref["skip"] == 0).sum())
+
+
 @pytest.mark.parametrize("degree", [0, 1, 2, 3])
 def test_every_sh_degree(degree):
     cloud = scenes.synth_v1(2000, 77, scale_factor=0.6)
