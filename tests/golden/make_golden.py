@@ -32,7 +32,10 @@ def main():
     logging.disable(logging.CRITICAL)
     if not ref_harness.reference_available():
         raise SystemExit("reference checkout not found; goldens can only be generated in the build container")
+    only = [a for a in sys.argv[1:] if a in CASES]       # `make_golden.py needles`: (re)generate the named scenes only
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         cloud, intr, view = build_case(c)
         with tempfile.TemporaryDirectory() as d:
             scenes.write_scene_dir(d, cloud, intr, [view])
@@ -53,6 +56,8 @@ def main():
         print(f"{name}: N={c['n']} {c['width']}x{c['height']} blended={out['n_blended']} ref={dt:.1f}s "
               f"unstable-vs-stable maxabs={float(keep['unstable_sort_maxabs']):.2e}")
 
+    if only:
+        return
     # gradients through the reference's own functions (small N)
     cloud, intr, view = build_case(GRAD_CASE)
     g = ref_harness.reference_autograd(cloud, intr, view, GRAD_CASE["degree"], grad_seed=3)
