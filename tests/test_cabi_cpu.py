@@ -132,6 +132,49 @@ def test_scene_io_round_trip(tmp_path):
     assert np.array_equal(sh.numpy(), cloud.sh_planar().transpose(2, 1, 0))
 
 
+def test_ply_reader_takes_every_format_plyfile_does(tmp_path):
+    """The reference reads its checkpoint through `plyfile` (rasterize.py:353), which accepts binary little / big endian
+    and ascii files.  The in-tree reader yields the same little-endian float32 columns for all three, plus mixed
+    property types, comments and a second element after the vertices; malformed files raise ValueError."""
+    import utils
+    from gsr_b200 import ply, scenes
+
+    cloud = scenes.synth_v1(37, 5)
+    table = cloud.ply_table()
+    base = str(tmp_path / "le.ply")
+    ply.write_gaussian_ply(base, table)
+    head = open(base, "rb").read().split(b"end_header\n")[0] + b"end_header\n"
+    head = head.replace(b"element vertex", b"comment written by a test\nelement vertex")
+    be, txt = str(tmp_path / "be.ply"), str(tmp_path / "ascii.ply")
+    open(be, "wb").write(head.replace(b"binary_little_endian", b"binary_big_endian") + table.astype(">f4").tobytes())
+    body = "\n".join(" ".join(repr(float(v)) for v in row) for row in table) + "\n"
+    open(txt, "wb").write(head.replace(b"binary_little_endian", b"ascii") + body.encode())
+    for path in (base, be, txt):
+        block, names = ply.read_vertex_block(path)
+        assert names == ply.GS_PROPERTIES and block.dtype == np.float32 and np.array_equal(block, table), path
+        data = ply.PlyData.read(path)
+        assert np.array_equal(data.elements[0]["opacity"], cloud.opacity)
+        assert np.array_equal(utils.read_color_components(data).numpy(), cloud.sh_planar().transpose(2, 1, 0))
+    # mixed property types and a trailing element (a mesh export): columns by name, faces ignored by the render path
+    mixed = str(tmp_path / "mixed.ply")
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex 3\nproperty double x\nproperty float y\n"
+           "property uchar red\nelement other 2\nproperty int a\nend_header\n").encode()
+    rec = np.zeros(3, dtype=[("x", "<f8"), ("y", "<f4"), ("red", "u1")])
+    rec["x"], rec["y"], rec["red"] = [1.5, -2.0, 3.25], [0.5, 0.25, 0.125], [7, 8, 9]
+    open(mixed, "wb").write(hdr + rec.tobytes() + np.array([4, 5], "<i4").tobytes())
+    data = ply.PlyData.read(mixed)
+    assert np.array_equal(data["vertex"]["x"], rec["x"]) and np.array_equal(data["vertex"]["red"], rec["red"])
+    assert np.array_equal(data["other"]["a"], [4, 5]) and len(data.elements[0]) == 3
+    with pytest.raises(ValueError):
+        ply.read_vertex_block(mixed)              # the device loader needs all-float32 vertices
+    for bad in (b"plx\n", head.replace(b"binary_little_endian", b"binary_middle_endian"), head + table.tobytes()[:-5],
+                head.replace(b"binary_little_endian", b"ascii") + body.encode()[: len(body) // 2].rsplit(b"\n", 1)[0] + b"\n"):
+        broken = str(tmp_path / "broken.ply")
+        open(broken, "wb").write(bad)
+        with pytest.raises(ValueError):
+            ply.PlyData.read(broken)
+
+
 def test_ground_truth_comparison_and_frame_writer_run_on_the_host(tmp_path):
     """The helpers around the path are plain host code: PSNR / side-by-side PNG against a photo and
     the frame-sequence writer need neither the library nor a GPU."""

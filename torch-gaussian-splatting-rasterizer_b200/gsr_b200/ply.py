@@ -1,4 +1,4 @@
-"""Minimal binary-little-endian PLY reader/writer for 3DGS point clouds.
+"""Minimal PLY reader (binary little / big endian, ascii) and binary-little-endian writer for 3DGS point clouds.
 
 The reference reads its Gaussians through the third-party ``plyfile`` package
 (/root/reference/rasterize.py:353, /root/reference/utils.py:21-27), which is not
@@ -95,15 +95,36 @@ def _read_elements(path: str) -> List[PlyElement]:
                 layout[-1]["props"].append((tok[2], _NP_OF_PLY[tok[1]]))
             elif tok[0] == "end_header":
                 break
-        if fmt != "binary_little_endian":
-            raise ValueError(f"{path}: only binary_little_endian PLY is supported (got {fmt})")
+        if fmt not in ("binary_little_endian", "binary_big_endian", "ascii"):
+            raise ValueError(f"{path}: unknown PLY format {fmt}")
         out = []
         for el in layout:
-            dt = np.dtype(el["props"])
-            buf = fh.read(dt.itemsize * el["count"])
-            if len(buf) != dt.itemsize * el["count"]:
+            native = np.dtype(el["props"])  # little-endian record: what every consumer (and the GPU unpack) expects
+            if fmt == "ascii":
+                # one vertex per line, properties separated by blanks (what plyfile writes with text=True)
+                rows = []
+                while len(rows) < el["count"]:
+                    line = fh.readline()
+                    if not line:
+                        raise ValueError(f"{path}: truncated element {el['name']}")
+                    if line.strip():
+                        rows.append(line.split())
+                arr = np.empty(el["count"], dtype=native)
+                if el["count"]:
+                    cols = list(zip(*rows))
+                    if len(cols) != len(native.names):
+                        raise ValueError(f"{path}: element {el['name']} has {len(cols)} columns, header says {len(native.names)}")
+                    for name, col in zip(native.names, cols):
+                        kind = native[name].kind
+                        arr[name] = np.array(col, dtype=np.float64 if kind == "f" else np.int64).astype(native[name])
+                out.append(PlyElement(el["name"], arr))
+                continue
+            file_dt = native if fmt == "binary_little_endian" else native.newbyteorder(">")
+            buf = fh.read(file_dt.itemsize * el["count"])
+            if len(buf) != file_dt.itemsize * el["count"]:
                 raise ValueError(f"{path}: truncated element {el['name']}")
-            out.append(PlyElement(el["name"], np.frombuffer(buf, dtype=dt, count=el["count"])))
+            arr = np.frombuffer(buf, dtype=file_dt, count=el["count"])
+            out.append(PlyElement(el["name"], arr if file_dt == native else arr.astype(native)))
         return out
 
 
