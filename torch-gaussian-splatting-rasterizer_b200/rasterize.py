@@ -242,7 +242,7 @@ def run_rasterization(input_dir: str, trained_model_path, output_path: Optional[
         frames = os.path.join(output_path, "images")
         os.makedirs(frames, exist_ok=True)
         n_blend = renderer.frame_info()["n_visible"]
-        step, snap = 0, None
+        step, snap = 0, image  # a scene in which nothing is blended still gets its (black) closing frames
         while step < n_blend:  # reference :448-452: a snapshot after blended Gaussian number step+1
             snap = renderer.render(model, cam, last_rank=step + 1)
             _save_png(snap, os.path.join(frames, f"image_iter_{str(step).zfill(7)}.png"))
